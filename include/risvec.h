@@ -1,0 +1,217 @@
+/*
+ * risvec.h -- C ABI of the B200-native batched RIS-VEC environment library.
+ *
+ * One handle = E independent env instances (V vehicles, M RIS elements each) resident in
+ * the HBM of ONE GPU.  Each entry point replaces, for all E instances at once, one method of
+ * the reference python class `Environ`; the reference has no FFI of its own,
+ * so the binding a reference maintainer would add is the ctypes stub in INTEGRATION.md.
+ * Citations: MARL = Simulation-MARL-BCD/Environment.py, SARL = Simulation-SARL/Environment.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative RISVEC_ERR_* code; the message of the
+ *     last failure on the calling thread is available from risvec_last_error();
+ *   - all pointer arguments of the non-`_host` functions are DEVICE pointers on the handle's GPU,
+ *     caller-owned, dense row-major with the shapes given below; NULL = "not supplied";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     asynchronous on it; calls on one handle must be externally serialised;
+ *   - there is no CPU fallback: creation fails when no sm_100 device is usable.
+ */
+#ifndef RISVEC_H
+#define RISVEC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RISVEC_ABI_VERSION 1
+
+enum {
+    RISVEC_OK = 0,
+    RISVEC_ERR_INVALID = -1,     /* bad argument (shape, NULL handle, ...) */
+    RISVEC_ERR_UNSUPPORTED = -2, /* size outside what the kernels cover (V > 32, M > 1024, ...) */
+    RISVEC_ERR_CUDA = -3,        /* CUDA runtime / launch failure */
+    RISVEC_ERR_NODEVICE = -4     /* no usable sm_100 device */
+};
+
+enum { RISVEC_VARIANT_MARL = 0, RISVEC_VARIANT_SARL = 1 };
+enum { RISVEC_CHANNEL_FREE = 0, RISVEC_CHANNEL_3GPP_UMI = 1, RISVEC_CHANNEL_3GPP_UMA = 2,
+       RISVEC_CHANNEL_UNKNOWN = 3 };
+
+/* vehicle heading codes (the reference stores the characters 'u','d','l','r') */
+enum { RISVEC_DIR_UP = 0, RISVEC_DIR_DOWN = 1, RISVEC_DIR_LEFT = 2, RISVEC_DIR_RIGHT = 3 };
+
+/* batched form of the ragged `noma_groups` list of MARL:331-372: one int32 per user */
+#define RISVEC_PARTNER_SINGLE (-1)       /* group of one (OMA)                                  */
+#define RISVEC_PARTNER_NONE (-2)         /* in no group, or in a group of size != 1,2 -> rate 0 */
+#define RISVEC_PARTNER_SECOND (1 << 16)  /* OR-ed onto the partner index of the user that is
+                                            listed SECOND in its pair (tie rule of MARL:355)   */
+
+#define RISVEC_MAX_LANES 8
+
+/* Scalar parameters.  Mirrors the attributes the reference drivers set on the env object
+ * (SURVEY.md 8b "attributes WRITTEN"); defaults are filled by risvec_default_params(). */
+typedef struct risvec_params {
+    /* map (MARL:57-64) */
+    int32_t n_up, n_down, n_left, n_right;
+    double up_lanes[RISVEC_MAX_LANES], down_lanes[RISVEC_MAX_LANES];
+    double left_lanes[RISVEC_MAX_LANES], right_lanes[RISVEC_MAX_LANES];
+    double width, height;
+    /* shared (MARL:101-105,156-158; SARL:64-78) */
+    double time_slow, time_fast, bandwidth, k, L, rate;
+    int32_t data_buf_size;
+    int32_t channel_model; /* RISVEC_CHANNEL_* (MARL:185) */
+    /* MARL (MARL:70-143,555) */
+    double noise_power, P_max, power_scale, f_local_max, f_edge_max, cycles_per_bit, cpu_share_floor;
+    double w_d, w_e, R_min_bpsHz, D_max_s, qos_penalty, reward_clip;
+    int32_t qos_enable;
+    int32_t _pad0;
+    double fc_GHz, shadow_std_los, shadow_std_nlos, rician_K_dB, veh_ant_gain;
+    /* SARL (SARL:80-83) */
+    double t_factor1, t_factor2, penalty1, penalty2;
+} risvec_params_t;
+
+/* State fields owned by the library, exposed as device pointers for zero-copy views. */
+enum risvec_field {
+    RISVEC_F_POS_X = 0,      /* f64 [E,V]  vehicles[i].position[0]                       */
+    RISVEC_F_POS_Y,          /* f64 [E,V]  vehicles[i].position[1]                       */
+    RISVEC_F_DIR,            /* i32 [E,V]  RISVEC_DIR_*                                  */
+    RISVEC_F_VEL,            /* i32 [E,V]  velocity (m/s)                                */
+    RISVEC_F_DIST,           /* f64 [E,V]  distances_R_i                                 */
+    RISVEC_F_ANGLE,          /* f64 [E,V]  angles_R_i                                    */
+    RISVEC_F_AMP,            /* f64 [E,V]  ro^2 / (d^alpha1 * dBR^alpha2)                */
+    RISVEC_F_THETA_RE,       /* f64 [E,M]  Re elements_phase_shift_complex               */
+    RISVEC_F_THETA_IM,       /* f64 [E,M]  Im elements_phase_shift_complex               */
+    RISVEC_F_PHASE_REAL,     /* f32 [E,M]  elements_phase_shift_real (radians)           */
+    RISVEC_F_GAINS,          /* f64 [E,V]  channel_gains                                 */
+    RISVEC_F_DATABUF,        /* f64 [E,V]  DataBuf (kbit)                                */
+    RISVEC_F_DATA_T,         /* f32 [E,V]  data_t                                        */
+    RISVEC_F_DATA_P,         /* f32 [E,V]  data_p                                        */
+    RISVEC_F_OVER_DATA,      /* f32 [E,V]  over_data                                     */
+    RISVEC_F_OVER_POWER,     /* f32 [E,V]  over_power of the last step                   */
+    RISVEC_F_RATE,           /* f32 [E,V]  vehicle_rate                                  */
+    RISVEC_F_DATA_R,         /* i32 [E,V]  data_r (last arrivals)                        */
+    RISVEC_F_REWARD_USER,    /* f32 [E,V]  per-user reward of the last step              */
+    RISVEC_F_REWARD,         /* f32 [E]    global reward of the last step                */
+    RISVEC_F_MECQ,           /* f64 [E]    mec_queue_cycles                              */
+    RISVEC_F_STATS,          /* f32 [E,RISVEC_NSTAT] last_* scalars of the last step     */
+    RISVEC_F_LAST_POWER,     /* f32 [E,2,V] last_power_W                                 */
+    RISVEC_F_STEP_CTR,       /* i64 [E]    steps taken (keys the on-device RNG)          */
+    RISVEC_F_COUNT
+};
+
+/* columns of RISVEC_F_STATS / of the per-step `stats` trace (MARL:612-614,636-656,677,706-711) */
+enum risvec_stat {
+    RISVEC_S_DELAY_MEAN = 0, RISVEC_S_ENERGY_MEAN, RISVEC_S_DELAY_LOCAL_MEAN, RISVEC_S_DELAY_EDGE_Q_MEAN,
+    RISVEC_S_DELAY_EDGE_C_MEAN, RISVEC_S_T_TX_MEAN, RISVEC_S_BACKLOG_KBIT_MEAN, RISVEC_S_MEC_UTILIZATION,
+    RISVEC_S_LOCAL_UTIL_MEAN, RISVEC_S_QOS_VIOLATION, RISVEC_S_OFF_KBIT_SUM, RISVEC_S_LOCAL_KBIT_SUM,
+    RISVEC_S_MEC_QUEUE_CYCLES, RISVEC_NSTAT_USED, RISVEC_NSTAT = 16
+};
+
+typedef struct risvec_env risvec_env_t;
+
+/* Per-step output traces of a MARL rollout; every member may be NULL (not written).
+ * What MARL:731 returns plus the attributes the driver reads after each step. */
+typedef struct risvec_marl_out {
+    float* reward_user; /* [T,E,V]   */
+    float* reward;      /* [T,E]     global_reward                       */
+    float* DataBuf;     /* [T,E,V]   after arrivals                      */
+    float* data_t;      /* [T,E,V]   */
+    float* data_p;      /* [T,E,V]   */
+    float* rate;        /* [T,E,V]   vehicle_rate                        */
+    float* over_power;  /* [T,E,V]   */
+    float* stats;       /* [T,E,RISVEC_NSTAT]                            */
+    float* last_power;  /* [T,E,2,V] last_power_W                        */
+} risvec_marl_out_t;
+
+/* Per-step output traces of a SARL rollout (SARL:359); every member may be NULL. */
+typedef struct risvec_sarl_out {
+    float* reward;     /* [T,E]   */
+    float* DataBuf;    /* [T,E,V] after arrivals */
+    float* data_t;     /* [T,E,V] */
+    float* data_p;     /* [T,E,V] */
+    float* over_power; /* [T,E,V] */
+    float* over_data;  /* [T,E,V] */
+    float* rate;       /* [T,E,V] */
+} risvec_sarl_out_t;
+
+int risvec_abi_version(void);
+const char* risvec_last_error(void);
+
+/* Reference class defaults (MARL:70-143 or SARL:64-83) and the drivers' lane constants
+ * (marl_train_bcd.py:446-449). */
+int risvec_default_params(int variant, risvec_params_t* out);
+
+/* Environ.__init__ (MARL:57-190, SARL:37-106) for E instances.  `env_index_base` is the global
+ * index of this shard's first env (keys the on-device RNG so results do not depend on how envs
+ * are sharded over GPUs); `seed` keys all on-device randomness. */
+int risvec_create(const risvec_params_t* params, int variant, int E, int V, int M, int control_bit, int device,
+                  uint64_t seed, int64_t env_index_base, risvec_env_t** out);
+int risvec_destroy(risvec_env_t* env);
+
+/* attribute writes of the drivers (marl_train_bcd.py:563-594,750-779) */
+int risvec_set_params(risvec_env_t* env, const risvec_params_t* params);
+int risvec_get_params(const risvec_env_t* env, risvec_params_t* out);
+
+/* zero-copy access to library-owned state; *rows x *cols elements of `*elem_bytes` bytes */
+int risvec_field(risvec_env_t* env, int field, void** dev_ptr, int64_t* rows, int64_t* cols, int* elem_bytes,
+                 int* is_float);
+
+/* make_new_game (MARL:733-737 + 381-410; SARL:361-365 + 176-205).
+ * reset_ints [E,n_ints] i32: the randint draws in the reference's call order
+ * (9 per round of four vehicles, 3 per extra vehicle, 1 for DataBuf); reset_dirs [E,V%4] i32
+ * heading codes of the extra vehicles.  Both NULL -> on-device Philox draws. */
+int risvec_make_new_game(risvec_env_t* env, const int32_t* reset_ints, int n_ints, const int32_t* reset_dirs,
+                         int n_dirs, void* stream);
+
+/* renew_positions (MARL:412-542).  uniforms [E,n] f64 consumed per env by a cursor in the
+ * reference's draw order (NULL -> Philox); used_out [E] i32 receives the draws consumed. */
+int risvec_renew_positions(risvec_env_t* env, const double* uniforms, int n, int32_t* used_out, void* stream);
+
+/* compute_parms (MARL:241-253) */
+int risvec_compute_parms(risvec_env_t* env, void* stream);
+
+/* get_next_phase (MARL:233-239): phase [E,M] f32 radians */
+int risvec_set_phase(risvec_env_t* env, const float* phase, void* stream);
+
+/* optimize_phase_shift (MARL:208-231), float64 */
+int risvec_optimize_phase_shift(risvec_env_t* env, void* stream);
+
+/* update_channel_gains (MARL:255-327).  For the 3GPP models: chan_rand [E,V] f64 U(0,1),
+ * chan_normal [E,V,3] f64 N(0,1) (shadowing, Rice re, Rice im), chan_exp [E,V] f64 Exp(1);
+ * all NULL -> Philox.  Ignored for RISVEC_CHANNEL_FREE. */
+int risvec_update_channel_gains(risvec_env_t* env, const double* chan_rand, const double* chan_normal,
+                                const double* chan_exp, void* stream);
+
+/* T consecutive Environ.step calls (MARL:547-731) fused in one launch; T = 1 is a plain step.
+ * action [T,E,2,V] f32; partner [E,V] i32 and ngroups [E] i32 (fixed over the T steps, see
+ * RISVEC_PARTNER_*); arrivals [T,E,V] i32 Poisson draws (NULL -> Philox). */
+int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int32_t* partner,
+                        const int32_t* ngroups, const int32_t* arrivals, const risvec_marl_out_t* out, void* stream);
+
+/* T consecutive SARL Environ.step calls (SARL:321-359).  action [T,E,2,V] f32,
+ * phase [T,E,M] f32 radians, arrivals [T,E,V] i32 (NULL -> Philox). */
+int risvec_rollout_sarl(risvec_env_t* env, int T, const float* action, const float* phase, const int32_t* arrivals,
+                        const risvec_sarl_out_t* out, void* stream);
+
+/* Same two calls with HOST buffers (pinned for full PCIe speed): inputs are copied to device
+ * staging owned by the handle, the rollout runs, the non-NULL traces are copied back.  All on
+ * `stream`; the caller synchronises the stream before reading the outputs. */
+int risvec_rollout_marl_host(risvec_env_t* env, int T, const float* action, const int32_t* partner,
+                             const int32_t* ngroups, const int32_t* arrivals, const risvec_marl_out_t* out,
+                             void* stream);
+int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, const float* phase,
+                             const int32_t* arrivals, const risvec_sarl_out_t* out, void* stream);
+
+/* Episode statistics for the multi-GPU reduction: sums over this shard's E envs of the
+ * RISVEC_F_STATS columns and of RISVEC_F_REWARD, written to out [RISVEC_NSTAT + 1] f64 (device). */
+int risvec_shard_stats(risvec_env_t* env, double* out, void* stream);
+
+/* number of kernels this handle has launched so far (bench.py reports it as gpu_launches) */
+int64_t risvec_launch_count(const risvec_env_t* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RISVEC_H */

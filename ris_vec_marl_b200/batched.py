@@ -1,0 +1,286 @@
+"""`BatchedEnviron`: E independent reference `Environ` instances stepped on one B200.
+
+Host-side mirror of the reference class (Simulation-MARL-BCD/Environment.py:56 and
+Simulation-SARL/Environment.py:36) with the same method names; every method is one call
+into the C ABI (include/risvec.h) and therefore one or a few sm_100a kernel launches.
+PyTorch is used only for device memory, streams and (in `dist.py`) NCCL.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CHANNEL, FIELDS, NSTAT, STAT_COLUMNS, VARIANT, MarlOut, Params, SarlOut, check
+
+_PARAM_NAMES = {n for n, _ in Params._fields_} - {"_pad0"}
+_LANE_FIELDS = ("up_lanes", "down_lanes", "left_lanes", "right_lanes")
+MARL_TRACES = ("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate", "over_power", "stats", "last_power")
+SARL_TRACES = ("reward", "DataBuf", "data_t", "data_p", "over_power", "over_data", "rate")
+
+
+class _DevView:
+    """Minimal `__cuda_array_interface__` holder so torch can alias library-owned memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def default_params(variant: str) -> Params:
+    p = Params()
+    check(_lib.load_library().risvec_default_params(VARIANT[variant], C.byref(p)))
+    return p
+
+
+def marl_yaml_overrides() -> dict:
+    """Values in force after marl_train_bcd.py:547-779 overlays config.yaml."""
+    n0 = 10 ** ((-174 - 30) / 10)
+    return dict(rate=1.0, f_local_max=3e9, f_edge_max=2e9, cycles_per_bit=300.0, k=1e-28, cpu_share_floor=0.10,
+                P_max=2.0, bandwidth=5.0, noise_power=n0 * (5.0 * 1e6), power_scale=0.7, w_d=1.0, w_e=1.0,
+                qos_enable=1, R_min_bpsHz=0.15, D_max_s=0.12, qos_penalty=1.5, reward_clip=50.0)
+
+
+def encode_groups(noma_groups, V):
+    """Ragged `noma_groups` of one env (Environment.py:339-370) -> (partner[V] int32, ngroups)."""
+    partner = np.full(V, _lib.PARTNER_NONE, dtype=np.int32)
+    for g in noma_groups:
+        if len(g) == 1:
+            partner[int(g[0])] = _lib.PARTNER_SINGLE
+        elif len(g) == 2:
+            partner[int(g[0])] = int(g[1])
+            partner[int(g[1])] = int(g[0]) | _lib.PARTNER_SECOND
+    return partner, len(noma_groups)
+
+
+class BatchedEnviron:
+    def __init__(self, variant, n_envs, n_veh=8, M=40, control_bit=3, device=0, seed=1234, env_index_base=0,
+                 lanes=None, width=None, height=None, **param_overrides):
+        if variant not in VARIANT:
+            raise ValueError("variant must be 'marl' or 'sarl'")
+        self._lib = _lib.load_library()  # raises if the CUDA library is absent: no fallback
+        if not torch.cuda.is_available():
+            raise _lib.RisvecLibraryError("no CUDA device: the batched env has no CPU path")
+        self.variant, self.E, self.V, self.M = variant, int(n_envs), int(n_veh), int(M)
+        self.control_bit = int(control_bit)
+        self.device = torch.device("cuda", int(device))
+        self.params = default_params(variant)
+        if lanes is not None:
+            for name, vals in zip(("down", "up", "left", "right"), lanes):
+                self._set_lanes(name, vals)
+        if width is not None:
+            self.params.width = float(width)
+        if height is not None:
+            self.params.height = float(height)
+        self._apply(param_overrides)
+        h = C.c_void_p()
+        check(self._lib.risvec_create(C.byref(self.params), VARIANT[variant], self.E, self.V, self.M, self.control_bit,
+                                      self.device.index, int(seed), int(env_index_base), C.byref(h)))
+        self._h = h
+        self._views = {}
+        for i, name in enumerate(FIELDS):
+            ptr, rows, cols, eb, fl = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int()
+            check(self._lib.risvec_field(self._h, i, C.byref(ptr), C.byref(rows), C.byref(cols), C.byref(eb),
+                                         C.byref(fl)))
+            typestr = ("<f" if fl.value else "<i") + str(eb.value)
+            shape = (rows.value, cols.value) if cols.value > 1 else (rows.value,)
+            self._views[name] = torch.as_tensor(_DevView(ptr.value, shape, typestr), device=self.device)
+        self._views["last_power_W"] = self._views["last_power_W"].view(self.E, 2, self.V)
+
+    # ------------------------------------------------------------------ params
+    def _set_lanes(self, name, vals):
+        vals = [float(v) for v in vals]
+        if not 1 <= len(vals) <= _lib.MAX_LANES:
+            raise ValueError("1..8 lanes per family")
+        arr = getattr(self.params, name + "_lanes")
+        for i, v in enumerate(vals):
+            arr[i] = v
+        setattr(self.params, "n_" + name, len(vals))
+
+    def _apply(self, kw):
+        for k, v in kw.items():
+            if k == "channel_model" and isinstance(v, str):
+                v = CHANNEL.get(v, 3)  # unknown keyword -> RISVEC_CHANNEL_UNKNOWN (Environment.py:315-317)
+            if k not in _PARAM_NAMES or k in _LANE_FIELDS:
+                raise AttributeError(f"unknown env parameter {k!r}")
+            setattr(self.params, k, type(getattr(self.params, k))(v))
+
+    def set_params(self, **kw):
+        """Attribute writes of the reference drivers (marl_train_bcd.py:563-594,750-779)."""
+        self._apply(kw)
+        check(self._lib.risvec_set_params(self._h, C.byref(self.params)))
+
+    def get_param(self, name):
+        return getattr(self.params, name)
+
+    # ------------------------------------------------------------------ helpers
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._views.clear()
+            self._lib.risvec_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, x, dtype, shape=None):
+        if x is None:
+            return None
+        t = torch.as_tensor(x)
+        if t.dtype != dtype or t.device != self.device or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=dtype).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+    def state(self, name):
+        """Zero-copy torch view of a library-owned state field (see `_lib.FIELDS`)."""
+        return self._views[name]
+
+    def __getattr__(self, name):
+        views = self.__dict__.get("_views")
+        if views is not None and name in views:
+            return views[name]
+        raise AttributeError(name)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.risvec_launch_count(self._h))
+
+    # ------------------------------------------------------------------ reference methods
+    def make_new_game(self, reset_ints=None, reset_dirs=None):
+        ri = self._dev(reset_ints, torch.int32)
+        rd = self._dev(reset_dirs, torch.int32)
+        n_i = 0 if ri is None else ri.shape[1]
+        n_d = 0 if rd is None or rd.numel() == 0 else rd.shape[1]
+        if rd is not None and rd.numel() == 0:
+            rd = None
+        check(self._lib.risvec_make_new_game(self._h, self._p(ri), n_i, self._p(rd), n_d, self.stream))
+
+    def renew_positions(self, uniforms=None):
+        u = self._dev(uniforms, torch.float64)
+        used = torch.empty(self.E, dtype=torch.int32, device=self.device)
+        n = 0 if u is None else u.shape[1]
+        check(self._lib.risvec_renew_positions(self._h, self._p(u), n, self._p(used), self.stream))
+        return used
+
+    def compute_parms(self):
+        check(self._lib.risvec_compute_parms(self._h, self.stream))
+
+    def get_next_phase(self, action_phase):
+        ph = self._dev(action_phase, torch.float32, (self.E, self.M))
+        check(self._lib.risvec_set_phase(self._h, self._p(ph), self.stream))
+
+    def optimize_phase_shift(self):
+        check(self._lib.risvec_optimize_phase_shift(self._h, self.stream))
+
+    def update_channel_gains(self, chan_rand=None, chan_normal=None, chan_exp=None):
+        r = self._dev(chan_rand, torch.float64)
+        n = self._dev(chan_normal, torch.float64)
+        x = self._dev(chan_exp, torch.float64)
+        check(self._lib.risvec_update_channel_gains(self._h, self._p(r), self._p(n), self._p(x), self.stream))
+
+    def get_channel_gains(self):
+        return self._views["gains"]
+
+    # ------------------------------------------------------------------ steps / rollouts
+    def _alloc_traces(self, names, T, all_names):
+        E, V = self.E, self.V
+        shapes = {"reward": (T, E), "stats": (T, E, NSTAT), "last_power": (T, E, 2, V)}
+        out = {}
+        for n in names:
+            if n not in all_names:
+                raise ValueError(f"unknown trace {n!r}")
+            out[n] = torch.empty(shapes.get(n, (T, E, V)), dtype=torch.float32, device=self.device)
+        return out
+
+    def rollout_marl(self, actions, partner, ngroups, arrivals=None, traces=MARL_TRACES, out=None):
+        """T fused Environ.step calls; actions [T,E,2,V]; returns {trace: tensor [T,...]}.
+        `out` may hold preallocated trace tensors (as made by `_alloc_traces`)."""
+        a = self._dev(actions, torch.float32)
+        T = a.shape[0]
+        if tuple(a.shape) != (T, self.E, 2, self.V):
+            raise ValueError(f"actions must be [T,{self.E},2,{self.V}]")
+        pt = self._dev(partner, torch.int32, (self.E, self.V))
+        ng = self._dev(ngroups, torch.int32, (self.E,))
+        ar = self._dev(arrivals, torch.int32, (T, self.E, self.V)) if arrivals is not None else None
+        if out is None:
+            out = self._alloc_traces(traces, T, MARL_TRACES)
+        o = MarlOut(**{k: v.data_ptr() for k, v in out.items()})
+        check(self._lib.risvec_rollout_marl(self._h, T, self._p(a), self._p(pt), self._p(ng), self._p(ar), C.byref(o),
+                                            self.stream))
+        return out
+
+    def rollout_sarl(self, actions, phases, arrivals=None, traces=SARL_TRACES, out=None):
+        a = self._dev(actions, torch.float32)
+        T = a.shape[0]
+        if tuple(a.shape) != (T, self.E, 2, self.V):
+            raise ValueError(f"actions must be [T,{self.E},2,{self.V}]")
+        ph = self._dev(phases, torch.float32, (T, self.E, self.M))
+        ar = self._dev(arrivals, torch.int32, (T, self.E, self.V)) if arrivals is not None else None
+        if out is None:
+            out = self._alloc_traces(traces, T, SARL_TRACES)
+        o = SarlOut(**{k: v.data_ptr() for k, v in out.items()})
+        check(self._lib.risvec_rollout_sarl(self._h, T, self._p(a), self._p(ph), self._p(ar), C.byref(o), self.stream))
+        return out
+
+    def step_marl(self, action, partner, ngroups, arrivals=None, traces=()):
+        a = self._dev(action, torch.float32, (self.E, 2, self.V))
+        ar = self._dev(arrivals, torch.int32, (self.E, self.V))[None] if arrivals is not None else None
+        return {k: v[0] for k, v in self.rollout_marl(a[None], partner, ngroups, ar, traces).items()}
+
+    def step_sarl(self, action, phase, arrivals=None, traces=()):
+        a = self._dev(action, torch.float32, (self.E, 2, self.V))
+        ph = self._dev(phase, torch.float32, (self.E, self.M))
+        ar = self._dev(arrivals, torch.int32, (self.E, self.V))[None] if arrivals is not None else None
+        return {k: v[0] for k, v in self.rollout_sarl(a[None], ph[None], ar, traces).items()}
+
+    # ---- host-buffer entry points (the end-to-end path: H2D + rollout + D2H on one stream)
+    @staticmethod
+    def _hp(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+    def rollout_sarl_host(self, actions, phases, arrivals, out):
+        """`actions/phases/arrivals` and the tensors in `out` are (pinned) HOST tensors."""
+        T = actions.shape[0]
+        o = SarlOut(**{k: v.data_ptr() for k, v in out.items()})
+        check(self._lib.risvec_rollout_sarl_host(self._h, T, self._hp(actions), self._hp(phases), self._hp(arrivals),
+                                                 C.byref(o), self.stream))
+
+    def rollout_marl_host(self, actions, partner, ngroups, arrivals, out):
+        T = actions.shape[0]
+        o = MarlOut(**{k: v.data_ptr() for k, v in out.items()})
+        check(self._lib.risvec_rollout_marl_host(self._h, T, self._hp(actions), self._hp(partner), self._hp(ngroups),
+                                                 self._hp(arrivals), C.byref(o), self.stream))
+
+    # ------------------------------------------------------------------ stats / checkpoint
+    def last_stats(self):
+        """{name: tensor [E]} of the reference's `last_*` attributes after the latest step."""
+        st = self._views["stats"]
+        return {n: st[:, i] for i, n in enumerate(STAT_COLUMNS)}
+
+    def shard_stats(self):
+        """f64 [NSTAT + 1] sums over this shard's envs (stats columns, then global reward)."""
+        out = torch.empty(NSTAT + 1, dtype=torch.float64, device=self.device)
+        check(self._lib.risvec_shard_stats(self._h, self._p(out), self.stream))
+        return out
+
+    def state_dict(self):
+        return {k: v.clone() for k, v in self._views.items()}
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            self._views[k].copy_(v.to(self.device))

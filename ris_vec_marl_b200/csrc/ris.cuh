@@ -1,0 +1,180 @@
+// RIS phase state, BCD phase optimiser and per-episode channel gains (float64).
+// Reference: Simulation-MARL-BCD/Environment.py:208-239,255-327.
+#pragma once
+#include "common.cuh"
+
+namespace risvec {
+
+// get_next_phase (MARL:233-239): theta_m = exp(j * phase_m), one thread per (env, element).
+__global__ void k_set_phase(Dims d, State s, const float* __restrict__ phase) {
+    const size_t ix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= (size_t)d.E * d.M) return;
+    const float ph = phase[ix];
+    double sn, cs;
+    sincos((double)ph, &sn, &cs);
+    s.phase_real[ix] = ph;
+    s.theta_re[ix] = cs;
+    s.theta_im[ix] = sn;
+}
+
+// Geometry phasor of vehicle v and element m:
+//   phases_R_i[v][m] * phase_R[m] = exp(-j*pi*angle_v*m) * exp(+j*pi*angle_BR*m)   (MARL:179,253)
+// evaluated as sincospi(m * (angle_BR - angle_v)) -- sincospi reduces its argument exactly.
+__device__ inline void geom_phasor(double delta, int m, double* re, double* im) {
+    sincospi((double)m * delta, im, re);
+}
+
+// optimize_phase_shift (MARL:208-231): one warp per env.
+// The reference objective sums `img` over ALL vehicles and elements (the same S for every
+// vehicle), so x(theta) = K * |S|^2 with S = sum_m theta_m c_m, c_m = sum_v phasor(v, m) and
+// K > 0 independent of theta.  The coordinate search therefore keeps S incrementally:
+// for each m the candidate maximising |S - theta_m c_m + e_k c_m|^2 wins, first maximum on
+// ties, accepted only if strictly positive (best starts at 0, MARL:210-218).
+__global__ void k_bcd(Dims d, State s) {
+    extern __shared__ double2 bcd_smem[];
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * wpb + warp;
+    if (e >= d.E) return;  // whole warp leaves together
+    const int V = d.V, M = d.M;
+    double2* c = bcd_smem + (size_t)warp * 2 * M;
+    double2* th = c + M;
+    double sr = 0.0, si = 0.0;
+    for (int m = lane; m < M; m += 32) {
+        double cr = 0.0, ci = 0.0;
+        for (int v = 0; v < V; ++v) {
+            double re, im;
+            geom_phasor(d.angle_BR - s.angle[(size_t)e * V + v], m, &re, &im);
+            cr += re;
+            ci += im;
+        }
+        const double tr = s.theta_re[(size_t)e * M + m], ti = s.theta_im[(size_t)e * M + m];
+        c[m] = make_double2(cr, ci);
+        th[m] = make_double2(tr, ti);
+        sr += tr * cr - ti * ci;
+        si += tr * ci + ti * cr;
+    }
+    sr = seg_sum<32>(sr);
+    si = seg_sum<32>(si);
+    __syncwarp();
+    for (int m = 0; m < M; ++m) {
+        const double2 cm = c[m], tm = th[m];
+        const double rr = sr - (tm.x * cm.x - tm.y * cm.y);
+        const double ri = si - (tm.x * cm.y + tm.y * cm.x);
+        // each lane scores candidates k = lane, lane + 32, ...
+        double best = -1.0, bsr = rr, bsi = ri, ber = 0.0, bei = 0.0;
+        int bk = 0x7fffffff;
+        for (int k = lane; k < d.ncand; k += 32) {
+            double er, ei;
+            sincospi(2.0 * (double)k / (double)d.ncand, &ei, &er);
+            const double cr = rr + (er * cm.x - ei * cm.y);
+            const double ci = ri + (er * cm.y + ei * cm.x);
+            const double val = cr * cr + ci * ci;
+            if (val > best) {
+                best = val; bk = k; bsr = cr; bsi = ci; ber = er; bei = ei;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(kFull, best, o);
+            const int ok = __shfl_xor_sync(kFull, bk, o);
+            const double osr = __shfl_xor_sync(kFull, bsr, o), osi = __shfl_xor_sync(kFull, bsi, o);
+            const double oer = __shfl_xor_sync(kFull, ber, o), oei = __shfl_xor_sync(kFull, bei, o);
+            if (ov > best || (ov == best && ok < bk)) {
+                best = ov; bk = ok; bsr = osr; bsi = osi; ber = oer; bei = oei;
+            }
+        }
+        if (best > 0.0) {
+            sr = bsr; si = bsi;
+            if (lane == 0) th[m] = make_double2(ber, bei);
+        } else {  // never improved on best = 0: the reference stores the integer 0
+            sr = rr; si = ri;
+            if (lane == 0) th[m] = make_double2(0.0, 0.0);
+        }
+        __syncwarp();
+    }
+    for (int m = lane; m < M; m += 32) {
+        s.theta_re[(size_t)e * M + m] = th[m].x;
+        s.theta_im[(size_t)e * M + m] = th[m].y;
+    }
+}
+
+// update_channel_gains, "free" model (MARL:263-273): the cascaded RIS reduction
+//   gain_v = amp_v * | sum_m theta_m * phasor(v, m) |^2
+// one warp per env, lanes stride over the M elements, complex warp-shuffle reduction.
+__global__ void k_gains_free(Dims d, State s) {
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * wpb + warp;
+    if (e >= d.E) return;
+    const int V = d.V, M = d.M;
+    for (int v = 0; v < V; ++v) {
+        const double delta = d.angle_BR - s.angle[(size_t)e * V + v];
+        double sr = 0.0, si = 0.0;
+        for (int m = lane; m < M; m += 32) {
+            double re, im;
+            geom_phasor(delta, m, &re, &im);
+            const double tr = s.theta_re[(size_t)e * M + m], ti = s.theta_im[(size_t)e * M + m];
+            sr += tr * re - ti * im;
+            si += tr * im + ti * re;
+        }
+        sr = seg_sum<32>(sr);
+        si = seg_sum<32>(si);
+        if (lane == 0) s.gains[(size_t)e * V + v] = s.amp[(size_t)e * V + v] * (sr * sr + si * si);
+    }
+}
+
+// update_channel_gains, simplified 3GPP TR 38.901 UMi / UMa branch (MARL:275-327): direct
+// vehicle<->BS link with LOS draw, log-normal shadowing and Rayleigh / Rice small-scale power.
+// One thread per (env, vehicle).  Draw order per vehicle in the reference: rand, normal,
+// then exponential (K = 0) or two normals.
+__global__ void k_gains_3gpp(Dims d, State s, risvec_params_t p, const double* __restrict__ c_rand,
+                             const double* __restrict__ c_normal, const double* __restrict__ c_exp,
+                             unsigned long long call) {
+    const size_t ix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= (size_t)d.E * d.V) return;
+    const int e = (int)(ix / d.V), v = (int)(ix % d.V);
+    double u, z0, z1, z2, ex;
+    if (c_rand != nullptr) {
+        u = c_rand[ix];
+        z0 = c_normal[ix * 3 + 0]; z1 = c_normal[ix * 3 + 1]; z2 = c_normal[ix * 3 + 2];
+        ex = c_exp[ix];
+    } else {
+        const uint4 a = rng_draw(d, e, call, (unsigned)(v * 4 + 0), kRngChannel);
+        const uint4 b = rng_draw(d, e, call, (unsigned)(v * 4 + 1), kRngChannel);
+        const uint4 c = rng_draw(d, e, call, (unsigned)(v * 4 + 2), kRngChannel);
+        u = u01d(a.x, a.y);
+        ex = -log1p(-u01d(a.z, a.w));
+        // Box-Muller pairs
+        const double r0 = sqrt(-2.0 * log1p(-u01d(b.x, b.y))), t0 = 2.0 * u01d(b.z, b.w);
+        const double r1 = sqrt(-2.0 * log1p(-u01d(c.x, c.y))), t1 = 2.0 * u01d(c.z, c.w);
+        z0 = r0 * cospi(t0); z1 = r0 * sinpi(t0); z2 = r1 * cospi(t1);
+        (void)t1;
+    }
+    const double dx = fabs(s.pos_x[ix] - kBsX), dy = fabs(s.pos_y[ix] - kBsY), dz = fabs(kBsZ - kVehZ);
+    const double d2d = hypot(dx, dy);
+    const double d3d = sqrt(d2d * d2d + dz * dz);
+    const bool los = u < 0.7 * exp(-d2d / 200.0);
+    const double dd = fmax(d3d, 1.0), fc = p.fc_GHz;
+    double pl = 0.0;
+    if (p.channel_model == RISVEC_CHANNEL_3GPP_UMI) {
+        pl = los ? 32.4 + 21.0 * log10(fc) + 20.0 * log10(dd) : 36.7 + 22.7 * log10(fc) + 26.0 * log10(dd);
+    } else if (p.channel_model == RISVEC_CHANNEL_3GPP_UMA) {
+        pl = los ? 28.0 + 22.0 * log10(fc) + 20.0 * log10(dd)
+                 : 13.54 + 39.08 * log10(dd) + 20.0 * log10(fc) - 0.6 * p.veh_ant_gain;
+    }
+    const double large = pow(10.0, -pl / 10.0);
+    const double shadow = pow(10.0, (z0 * (los ? p.shadow_std_los : p.shadow_std_nlos)) / 10.0);
+    double small;
+    if (p.rician_K_dB <= 1e-6) {
+        small = ex;
+    } else {
+        const double K = pow(10.0, p.rician_K_dB / 10.0);
+        const double sm = sqrt(K / (K + 1.0)), sg = 1.0 / sqrt(2.0 * (K + 1.0));
+        const double hr = sm + sg * z1, hi = sg * z2;
+        small = hr * hr + hi * hi;
+    }
+    s.gains[ix] = large * shadow * small;
+}
+
+}  // namespace risvec

@@ -1,0 +1,520 @@
+// C ABI of the risvec library (include/risvec.h): handle, state arena, launches.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "geom.cuh"
+#include "ris.cuh"
+#include "step.cuh"
+
+using namespace risvec;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return fail(RISVEC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct FieldDesc {
+    size_t offset;
+    int64_t rows, cols;
+    int elem_bytes, is_float;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int pow2ceil(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+struct risvec_env {
+    Dims dims;
+    State st;
+    risvec_params_t params;
+    int device;
+    char* arena;
+    size_t arena_bytes;
+    FieldDesc fields[RISVEC_F_COUNT];
+    unsigned long long reset_calls, mob_calls, chan_calls;
+    int64_t launches;
+    // device staging for the *_host entry points (grow-only)
+    char* stage;
+    size_t stage_bytes;
+};
+
+namespace {
+
+int check_launch(risvec_env* env, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RISVEC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    env->launches += 1;
+    return RISVEC_OK;
+}
+
+int validate_params(const risvec_params_t* p) {
+    if (p->n_up < 1 || p->n_down < 1 || p->n_left < 1 || p->n_right < 1 || p->n_up > RISVEC_MAX_LANES ||
+        p->n_down > RISVEC_MAX_LANES || p->n_left > RISVEC_MAX_LANES || p->n_right > RISVEC_MAX_LANES)
+        return fail(RISVEC_ERR_INVALID, "lane counts must be in [1, %d]", RISVEC_MAX_LANES);
+    if (!(p->time_fast > 0) || !(p->time_slow > 0)) return fail(RISVEC_ERR_INVALID, "time_fast/time_slow must be > 0");
+    if (p->data_buf_size - 1 <= 5) return fail(RISVEC_ERR_INVALID, "data_buf_size must be > 6");
+    return RISVEC_OK;
+}
+
+void bind_state(risvec_env* env) {
+    auto P = [&](int f) { return (void*)(env->arena + env->fields[f].offset); };
+    State& s = env->st;
+    s.pos_x = (double*)P(RISVEC_F_POS_X); s.pos_y = (double*)P(RISVEC_F_POS_Y);
+    s.dir = (int*)P(RISVEC_F_DIR); s.vel = (int*)P(RISVEC_F_VEL);
+    s.dist = (double*)P(RISVEC_F_DIST); s.angle = (double*)P(RISVEC_F_ANGLE); s.amp = (double*)P(RISVEC_F_AMP);
+    s.theta_re = (double*)P(RISVEC_F_THETA_RE); s.theta_im = (double*)P(RISVEC_F_THETA_IM);
+    s.phase_real = (float*)P(RISVEC_F_PHASE_REAL);
+    s.gains = (double*)P(RISVEC_F_GAINS); s.databuf = (double*)P(RISVEC_F_DATABUF);
+    s.data_t = (float*)P(RISVEC_F_DATA_T); s.data_p = (float*)P(RISVEC_F_DATA_P);
+    s.over_data = (float*)P(RISVEC_F_OVER_DATA); s.over_power = (float*)P(RISVEC_F_OVER_POWER);
+    s.rate = (float*)P(RISVEC_F_RATE); s.data_r = (int*)P(RISVEC_F_DATA_R);
+    s.reward_user = (float*)P(RISVEC_F_REWARD_USER); s.reward = (float*)P(RISVEC_F_REWARD);
+    s.mecq = (double*)P(RISVEC_F_MECQ); s.stats = (float*)P(RISVEC_F_STATS);
+    s.last_power = (float*)P(RISVEC_F_LAST_POWER); s.step_ctr = (long long*)P(RISVEC_F_STEP_CTR);
+}
+
+int ensure_stage(risvec_env* env, size_t bytes) {
+    if (bytes <= env->stage_bytes) return RISVEC_OK;
+    if (env->stage) cudaFree(env->stage);
+    env->stage = nullptr;
+    env->stage_bytes = 0;
+    CUDA_TRY(cudaMalloc((void**)&env->stage, bytes));
+    env->stage_bytes = bytes;
+    return RISVEC_OK;
+}
+
+// -------------------------------------------------------------------------- launch helpers
+template <int VP>
+int launch_marl(risvec_env* env, const MarlArgs& a, cudaStream_t st) {
+    const int threads = 128;
+    const long long total = (long long)env->dims.E * VP;
+    const int blocks = (int)((total + threads - 1) / threads);
+    k_marl_rollout<VP><<<blocks, threads, 0, st>>>(env->dims, env->st, env->params, a);
+    return check_launch(env, "k_marl_rollout");
+}
+
+template <int VP, int MPL, int WPE>
+int launch_sarl_cfg(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
+    constexpr int EPW = 32 / VP;
+    const int blocks = (env->dims.E + EPW - 1) / EPW;
+    const size_t smem = ((size_t)EPW * (env->dims.M + 2) + (WPE > 1 ? WPE * 32 : 0)) * sizeof(float2);
+    auto kern = k_sarl_rollout<VP, MPL, WPE>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, 32 * WPE, smem, st>>>(env->dims, env->st, env->params, a);
+    return check_launch(env, "k_sarl_rollout");
+}
+
+template <int VP>
+int launch_sarl(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
+    const int M = env->dims.M;
+    // elements per lane: M / WPE, register-resident table of MPL complex floats
+    if (M <= 16) return launch_sarl_cfg<VP, 16, 1>(env, a, st);
+    if (M <= 40) return launch_sarl_cfg<VP, 40, 1>(env, a, st);
+    if (M <= 64) return launch_sarl_cfg<VP, 32, 2>(env, a, st);
+    if (M <= 128) return launch_sarl_cfg<VP, 32, 4>(env, a, st);
+    if (M <= 256) return launch_sarl_cfg<VP, 32, 8>(env, a, st);
+    if (M <= 512) return launch_sarl_cfg<VP, 32, 16>(env, a, st);
+    if (M <= 1024) return launch_sarl_cfg<VP, 64, 16>(env, a, st);
+    return fail(RISVEC_ERR_UNSUPPORTED, "M = %d > 1024 is not covered by the SARL rollout kernel", M);
+}
+
+struct Carver {
+    char* base;
+    size_t off;
+    template <typename T>
+    T* take(size_t n) {
+        T* p = (T*)(base + off);
+        off = align_up(off + n * sizeof(T), 256);
+        return p;
+    }
+};
+
+__global__ void k_shard_stats(Dims d, State s, double* out) {
+    // one block; column c of the stats (and the reward as column NSTAT) summed over envs
+    __shared__ double red[32];
+    for (int c = 0; c <= RISVEC_NSTAT; ++c) {
+        double acc = 0.0;
+        for (int e = threadIdx.x; e < d.E; e += blockDim.x)
+            acc += (c < RISVEC_NSTAT) ? (double)s.stats[(size_t)e * RISVEC_NSTAT + c] : (double)s.reward[e];
+        acc = seg_sum<32>(acc);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+            v = seg_sum<32>(v);
+            if (threadIdx.x == 0) out[c] = v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// ======================================================================================
+extern "C" {
+
+int risvec_abi_version(void) { return RISVEC_ABI_VERSION; }
+const char* risvec_last_error(void) { return g_err; }
+
+int risvec_default_params(int variant, risvec_params_t* p) {
+    if (!p) return fail(RISVEC_ERR_INVALID, "params is NULL");
+    memset(p, 0, sizeof(*p));
+    // lane constants of the drivers (marl_train_bcd.py:446-449, ddpg_train.py:17-20)
+    const double up[4] = {(400 + 3.5 / 2) / 2.0, (400 + 3.5 + 3.5 / 2) / 2.0, (800 + 3.5 / 2) / 2.0,
+                          (800 + 3.5 + 3.5 / 2) / 2.0};
+    const double down[4] = {(400 - 3.5 - 3.5 / 2) / 2.0, (400 - 3.5 / 2) / 2.0, (800 - 3.5 - 3.5 / 2) / 2.0,
+                            (800 - 3.5 / 2) / 2.0};
+    p->n_up = p->n_down = p->n_left = p->n_right = 4;
+    for (int i = 0; i < 4; ++i) {
+        p->up_lanes[i] = up[i]; p->left_lanes[i] = up[i];
+        p->down_lanes[i] = down[i]; p->right_lanes[i] = down[i];
+    }
+    p->width = 400; p->height = 400;
+    p->time_slow = 0.1; p->time_fast = 0.001; p->bandwidth = 1.0; p->k = 1e-28; p->L = 500.0; p->rate = 3.0;
+    p->data_buf_size = 10;
+    p->channel_model = RISVEC_CHANNEL_FREE;
+    p->noise_power = pow(10.0, (-174.0 - 30.0) / 10.0) * 1.0e6;  // MARL:74-76
+    p->P_max = 1.0; p->power_scale = 0.7; p->f_local_max = 1.0e9; p->f_edge_max = 2.0e9; p->cycles_per_bit = 500.0;
+    p->cpu_share_floor = 0.10; p->w_d = 0.5; p->w_e = 3.0; p->R_min_bpsHz = 0.20; p->D_max_s = 0.10;
+    p->qos_penalty = 5.0; p->reward_clip = 50.0; p->qos_enable = 1;
+    p->fc_GHz = 3.5; p->shadow_std_los = 4.0; p->shadow_std_nlos = 7.0; p->rician_K_dB = 0.0; p->veh_ant_gain = 3.0;
+    p->t_factor1 = 1.0; p->t_factor2 = 0.6; p->penalty1 = 2.0; p->penalty2 = 2.0;
+    (void)variant;
+    return RISVEC_OK;
+}
+
+int risvec_create(const risvec_params_t* params, int variant, int E, int V, int M, int control_bit, int device,
+                  uint64_t seed, int64_t env_index_base, risvec_env_t** out) {
+    if (!out) return fail(RISVEC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!params) return fail(RISVEC_ERR_INVALID, "params is NULL");
+    if (variant != RISVEC_VARIANT_MARL && variant != RISVEC_VARIANT_SARL)
+        return fail(RISVEC_ERR_INVALID, "unknown variant %d", variant);
+    if (E < 1 || V < 1 || M < 1) return fail(RISVEC_ERR_INVALID, "E, V, M must be >= 1 (got %d, %d, %d)", E, V, M);
+    if (control_bit < 0 || control_bit > 10) return fail(RISVEC_ERR_INVALID, "control_bit must be in [0, 10]");
+    if (V > 32) return fail(RISVEC_ERR_UNSUPPORTED, "V = %d > 32 vehicles per env is not covered by the kernels", V);
+    if (M > 1024) return fail(RISVEC_ERR_UNSUPPORTED, "M = %d > 1024 RIS elements is not covered by the kernels", M);
+    if (int rc = validate_params(params)) return rc;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(RISVEC_ERR_NODEVICE, "no CUDA device visible: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(RISVEC_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RISVEC_ERR_NODEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device,
+                    prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+
+    risvec_env* env = new (std::nothrow) risvec_env();
+    if (!env) return fail(RISVEC_ERR_INVALID, "out of host memory");
+    memset(env, 0, sizeof(*env));
+    env->device = device;
+    env->params = *params;
+    Dims& d = env->dims;
+    d.E = E; d.V = V; d.M = M; d.ncand = 1 << control_bit; d.variant = variant;
+    d.seed = seed; d.env_base = env_index_base;
+    d.dist_BR = sqrt((kBsX - kRisX) * (kBsX - kRisX) + (kBsY - kRisY) * (kBsY - kRisY) + (kBsZ - kRisZ) * (kBsZ - kRisZ));
+    d.angle_BR = (kRisX - kBsX) / d.dist_BR;  // MARL:175-177
+
+    struct Spec { int f; int64_t rows, cols; int eb, fl; };
+    const int64_t EV = (int64_t)E * V;
+    (void)EV;
+    const Spec specs[RISVEC_F_COUNT] = {
+        {RISVEC_F_POS_X, E, V, 8, 1}, {RISVEC_F_POS_Y, E, V, 8, 1}, {RISVEC_F_DIR, E, V, 4, 0},
+        {RISVEC_F_VEL, E, V, 4, 0}, {RISVEC_F_DIST, E, V, 8, 1}, {RISVEC_F_ANGLE, E, V, 8, 1},
+        {RISVEC_F_AMP, E, V, 8, 1}, {RISVEC_F_THETA_RE, E, M, 8, 1}, {RISVEC_F_THETA_IM, E, M, 8, 1},
+        {RISVEC_F_PHASE_REAL, E, M, 4, 1}, {RISVEC_F_GAINS, E, V, 8, 1}, {RISVEC_F_DATABUF, E, V, 8, 1},
+        {RISVEC_F_DATA_T, E, V, 4, 1}, {RISVEC_F_DATA_P, E, V, 4, 1}, {RISVEC_F_OVER_DATA, E, V, 4, 1},
+        {RISVEC_F_OVER_POWER, E, V, 4, 1}, {RISVEC_F_RATE, E, V, 4, 1}, {RISVEC_F_DATA_R, E, V, 4, 0},
+        {RISVEC_F_REWARD_USER, E, V, 4, 1}, {RISVEC_F_REWARD, E, 1, 4, 1}, {RISVEC_F_MECQ, E, 1, 8, 1},
+        {RISVEC_F_STATS, E, RISVEC_NSTAT, 4, 1}, {RISVEC_F_LAST_POWER, E, 2 * V, 4, 1},
+        {RISVEC_F_STEP_CTR, E, 1, 8, 0}};
+    size_t off = 0;
+    for (int i = 0; i < RISVEC_F_COUNT; ++i) {
+        const Spec& sp = specs[i];
+        env->fields[sp.f] = {off, sp.rows, sp.cols, sp.eb, sp.fl};
+        off = align_up(off + (size_t)sp.rows * sp.cols * sp.eb, 256);
+    }
+    env->arena_bytes = off;
+    cudaError_t ce = cudaMalloc((void**)&env->arena, env->arena_bytes);
+    if (ce != cudaSuccess) {
+        delete env;
+        return fail(RISVEC_ERR_CUDA, "cudaMalloc(%zu bytes of env state): %s", off, cudaGetErrorString(ce));
+    }
+    ce = cudaMemset(env->arena, 0, env->arena_bytes);  // Environ.__init__ zero-fills everything
+    if (ce != cudaSuccess) {
+        cudaFree(env->arena);
+        delete env;
+        return fail(RISVEC_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(ce));
+    }
+    bind_state(env);
+    *out = env;
+    return RISVEC_OK;
+}
+
+int risvec_destroy(risvec_env_t* env) {
+    if (!env) return RISVEC_OK;
+    cudaSetDevice(env->device);
+    if (env->arena) cudaFree(env->arena);
+    if (env->stage) cudaFree(env->stage);
+    delete env;
+    return RISVEC_OK;
+}
+
+int risvec_set_params(risvec_env_t* env, const risvec_params_t* params) {
+    if (!env || !params) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    if (int rc = validate_params(params)) return rc;
+    env->params = *params;
+    return RISVEC_OK;
+}
+
+int risvec_get_params(const risvec_env_t* env, risvec_params_t* out) {
+    if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    *out = env->params;
+    return RISVEC_OK;
+}
+
+int risvec_field(risvec_env_t* env, int field, void** dev_ptr, int64_t* rows, int64_t* cols, int* elem_bytes,
+                 int* is_float) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (field < 0 || field >= RISVEC_F_COUNT) return fail(RISVEC_ERR_INVALID, "unknown field %d", field);
+    const FieldDesc& f = env->fields[field];
+    if (dev_ptr) *dev_ptr = env->arena + f.offset;
+    if (rows) *rows = f.rows;
+    if (cols) *cols = f.cols;
+    if (elem_bytes) *elem_bytes = f.elem_bytes;
+    if (is_float) *is_float = f.is_float;
+    return RISVEC_OK;
+}
+
+int risvec_make_new_game(risvec_env_t* env, const int32_t* reset_ints, int n_ints, const int32_t* reset_dirs,
+                         int n_dirs, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    const int V = env->dims.V;
+    const int need = 9 * (V / 4) + 3 * (V % 4) + 1;
+    if (reset_ints != nullptr && n_ints < need)
+        return fail(RISVEC_ERR_INVALID, "reset_ints needs %d draws per env for V = %d (got %d)", need, V, n_ints);
+    if (reset_ints != nullptr && (V % 4) != 0 && (reset_dirs == nullptr || n_dirs < V % 4))
+        return fail(RISVEC_ERR_INVALID, "reset_dirs needs %d headings per env", V % 4);
+    if (reset_ints == nullptr && reset_dirs != nullptr)
+        return fail(RISVEC_ERR_INVALID, "reset_dirs given without reset_ints");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const int threads = 128, blocks = (env->dims.E + threads - 1) / threads;
+    k_make_new_game<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, reset_ints, n_ints,
+                                                                  reset_dirs, n_dirs, env->reset_calls++);
+    return check_launch(env, "k_make_new_game");
+}
+
+int risvec_renew_positions(risvec_env_t* env, const double* uniforms, int n, int32_t* used_out, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (uniforms != nullptr && n < 1) return fail(RISVEC_ERR_INVALID, "uniforms given with n = %d", n);
+    CUDA_TRY(cudaSetDevice(env->device));
+    const int threads = 128, blocks = (env->dims.E + threads - 1) / threads;
+    k_renew_positions<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, uniforms, n,
+                                                                    used_out, env->mob_calls++);
+    return check_launch(env, "k_renew_positions");
+}
+
+int risvec_compute_parms(risvec_env_t* env, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const long long n = (long long)env->dims.E * env->dims.V;
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    k_compute_parms<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st);
+    return check_launch(env, "k_compute_parms");
+}
+
+int risvec_set_phase(risvec_env_t* env, const float* phase, void* stream) {
+    if (!env || !phase) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const long long n = (long long)env->dims.E * env->dims.M;
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    k_set_phase<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st, phase);
+    return check_launch(env, "k_set_phase");
+}
+
+int risvec_optimize_phase_shift(risvec_env_t* env, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const int wpb = 4, threads = 32 * wpb, blocks = (env->dims.E + wpb - 1) / wpb;
+    const size_t smem = (size_t)wpb * 2 * env->dims.M * sizeof(double2);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(k_bcd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bcd<<<blocks, threads, smem, (cudaStream_t)stream>>>(env->dims, env->st);
+    return check_launch(env, "k_bcd");
+}
+
+int risvec_update_channel_gains(risvec_env_t* env, const double* chan_rand, const double* chan_normal,
+                                const double* chan_exp, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(env->device));
+    if (env->params.channel_model == RISVEC_CHANNEL_FREE) {
+        const int wpb = 4, threads = 32 * wpb, blocks = (env->dims.E + wpb - 1) / wpb;
+        k_gains_free<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st);
+        return check_launch(env, "k_gains_free");
+    }
+    const bool any = chan_rand || chan_normal || chan_exp;
+    if (any && !(chan_rand && chan_normal && chan_exp))
+        return fail(RISVEC_ERR_INVALID, "chan_rand, chan_normal and chan_exp must be given together");
+    const long long n = (long long)env->dims.E * env->dims.V;
+    const int threads = 128, blocks = (int)((n + threads - 1) / threads);
+    k_gains_3gpp<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, chan_rand, chan_normal,
+                                                               chan_exp, env->chan_calls++);
+    return check_launch(env, "k_gains_3gpp");
+}
+
+int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int32_t* partner, const int32_t* ngroups,
+                        const int32_t* arrivals, const risvec_marl_out_t* out, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (env->dims.variant != RISVEC_VARIANT_MARL) return fail(RISVEC_ERR_INVALID, "handle is not a MARL env");
+    if (T < 1) return fail(RISVEC_ERR_INVALID, "T must be >= 1 (got %d)", T);
+    if (!action || !partner || !ngroups) return fail(RISVEC_ERR_INVALID, "action, partner and ngroups are required");
+    CUDA_TRY(cudaSetDevice(env->device));
+    MarlArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = T; a.action = action; a.partner = partner; a.ngroups = ngroups; a.arrivals = arrivals;
+    if (out) a.out = *out;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pow2ceil(env->dims.V)) {
+        case 1: return launch_marl<1>(env, a, st);
+        case 2: return launch_marl<2>(env, a, st);
+        case 4: return launch_marl<4>(env, a, st);
+        case 8: return launch_marl<8>(env, a, st);
+        case 16: return launch_marl<16>(env, a, st);
+        default: return launch_marl<32>(env, a, st);
+    }
+}
+
+int risvec_rollout_sarl(risvec_env_t* env, int T, const float* action, const float* phase, const int32_t* arrivals,
+                        const risvec_sarl_out_t* out, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (env->dims.variant != RISVEC_VARIANT_SARL) return fail(RISVEC_ERR_INVALID, "handle is not a SARL env");
+    if (T < 1) return fail(RISVEC_ERR_INVALID, "T must be >= 1 (got %d)", T);
+    if (!action || !phase) return fail(RISVEC_ERR_INVALID, "action and phase are required");
+    CUDA_TRY(cudaSetDevice(env->device));
+    SarlArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = T; a.action = action; a.phase = phase; a.arrivals = arrivals;
+    if (out) a.out = *out;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pow2ceil(env->dims.V)) {
+        case 1: return launch_sarl<1>(env, a, st);
+        case 2: return launch_sarl<2>(env, a, st);
+        case 4: return launch_sarl<4>(env, a, st);
+        case 8: return launch_sarl<8>(env, a, st);
+        case 16: return launch_sarl<16>(env, a, st);
+        default: return launch_sarl<32>(env, a, st);
+    }
+}
+
+// ---- host-buffer variants: H2D staging -> rollout -> D2H of the requested traces
+int risvec_rollout_marl_host(risvec_env_t* env, int T, const float* action, const int32_t* partner,
+                             const int32_t* ngroups, const int32_t* arrivals, const risvec_marl_out_t* out,
+                             void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (T < 1 || !action || !partner || !ngroups) return fail(RISVEC_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const size_t E = env->dims.E, V = env->dims.V, TE = (size_t)T * E;
+    const size_t n_act = TE * 2 * V, n_ev = TE * V;
+    size_t need = 256 * 16 + 4 * (n_act + E * V + E + n_ev) + 4 * (6 * n_ev + TE + TE * RISVEC_NSTAT + n_act);
+    if (int rc = ensure_stage(env, need)) return rc;
+    Carver c{env->stage, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d_act = c.take<float>(n_act);
+    int* d_part = c.take<int>(E * V);
+    int* d_ng = c.take<int>(E);
+    int* d_arr = arrivals ? c.take<int>(n_ev) : nullptr;
+    CUDA_TRY(cudaMemcpyAsync(d_act, action, n_act * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_part, partner, E * V * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ng, ngroups, E * 4, cudaMemcpyHostToDevice, st));
+    if (arrivals) CUDA_TRY(cudaMemcpyAsync(d_arr, arrivals, n_ev * 4, cudaMemcpyHostToDevice, st));
+    risvec_marl_out_t d_out;
+    memset(&d_out, 0, sizeof(d_out));
+    risvec_marl_out_t h = out ? *out : d_out;
+    if (h.reward_user) d_out.reward_user = c.take<float>(n_ev);
+    if (h.reward) d_out.reward = c.take<float>(TE);
+    if (h.DataBuf) d_out.DataBuf = c.take<float>(n_ev);
+    if (h.data_t) d_out.data_t = c.take<float>(n_ev);
+    if (h.data_p) d_out.data_p = c.take<float>(n_ev);
+    if (h.rate) d_out.rate = c.take<float>(n_ev);
+    if (h.over_power) d_out.over_power = c.take<float>(n_ev);
+    if (h.stats) d_out.stats = c.take<float>(TE * RISVEC_NSTAT);
+    if (h.last_power) d_out.last_power = c.take<float>(n_act);
+    if (int rc = risvec_rollout_marl(env, T, d_act, d_part, d_ng, d_arr, &d_out, stream)) return rc;
+#define D2H(member, count) \
+    if (h.member) CUDA_TRY(cudaMemcpyAsync(h.member, d_out.member, (count) * 4, cudaMemcpyDeviceToHost, st))
+    D2H(reward_user, n_ev); D2H(reward, TE); D2H(DataBuf, n_ev); D2H(data_t, n_ev); D2H(data_p, n_ev);
+    D2H(rate, n_ev); D2H(over_power, n_ev); D2H(stats, TE * RISVEC_NSTAT); D2H(last_power, n_act);
+    return RISVEC_OK;
+}
+
+int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, const float* phase,
+                             const int32_t* arrivals, const risvec_sarl_out_t* out, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (T < 1 || !action || !phase) return fail(RISVEC_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const size_t E = env->dims.E, V = env->dims.V, M = env->dims.M, TE = (size_t)T * E;
+    const size_t n_act = TE * 2 * V, n_ev = TE * V, n_ph = TE * M;
+    size_t need = 256 * 16 + 4 * (n_act + n_ph + n_ev) + 4 * (6 * n_ev + TE);
+    if (int rc = ensure_stage(env, need)) return rc;
+    Carver c{env->stage, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d_act = c.take<float>(n_act);
+    float* d_ph = c.take<float>(n_ph);
+    int* d_arr = arrivals ? c.take<int>(n_ev) : nullptr;
+    CUDA_TRY(cudaMemcpyAsync(d_act, action, n_act * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ph, phase, n_ph * 4, cudaMemcpyHostToDevice, st));
+    if (arrivals) CUDA_TRY(cudaMemcpyAsync(d_arr, arrivals, n_ev * 4, cudaMemcpyHostToDevice, st));
+    risvec_sarl_out_t d_out;
+    memset(&d_out, 0, sizeof(d_out));
+    risvec_sarl_out_t h = out ? *out : d_out;
+    if (h.reward) d_out.reward = c.take<float>(TE);
+    if (h.DataBuf) d_out.DataBuf = c.take<float>(n_ev);
+    if (h.data_t) d_out.data_t = c.take<float>(n_ev);
+    if (h.data_p) d_out.data_p = c.take<float>(n_ev);
+    if (h.over_power) d_out.over_power = c.take<float>(n_ev);
+    if (h.over_data) d_out.over_data = c.take<float>(n_ev);
+    if (h.rate) d_out.rate = c.take<float>(n_ev);
+    if (int rc = risvec_rollout_sarl(env, T, d_act, d_ph, d_arr, &d_out, stream)) return rc;
+    D2H(reward, TE); D2H(DataBuf, n_ev); D2H(data_t, n_ev); D2H(data_p, n_ev); D2H(over_power, n_ev);
+    D2H(over_data, n_ev); D2H(rate, n_ev);
+#undef D2H
+    return RISVEC_OK;
+}
+
+int risvec_shard_stats(risvec_env_t* env, double* out, void* stream) {
+    if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(env->device));
+    k_shard_stats<<<1, 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
+    return check_launch(env, "k_shard_stats");
+}
+
+int64_t risvec_launch_count(const risvec_env_t* env) { return env ? env->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,409 @@
+// Fused T-step rollouts of Environ.step for E env instances (T = 1 is a plain step).
+// Reference: Simulation-MARL-BCD/Environment.py:331-372,547-731 and
+//            Simulation-SARL/Environment.py:149-171,318-359.
+//
+// Thread mapping: an env owns VP = pow2ceil(V) adjacent lanes of one warp (lane v = vehicle v),
+// so a warp carries 32 / VP envs and every cross-vehicle term (NOMA partner lookup, sum of edge
+// cycles, means) is a segmented warp shuffle.  State (DataBuf, MEC queue, gains, phasor table)
+// lives in registers for the whole rollout; per step only actions / phases / arrivals stream
+// in from HBM and the requested traces stream out.
+#pragma once
+#include "common.cuh"
+
+namespace risvec {
+
+struct MarlArgs {
+    int T;
+    const float* action;   // [T,E,2,V]
+    const int* partner;    // [E,V]
+    const int* ngroups;    // [E]
+    const int* arrivals;   // [T,E,V] or null
+    risvec_marl_out_t out;
+};
+
+struct SarlArgs {
+    int T;
+    const float* action;  // [T,E,2,V]
+    const float* phase;   // [T,E,M]
+    const int* arrivals;  // [T,E,V] or null
+    risvec_sarl_out_t out;
+};
+
+__device__ inline int draw_arrival(const Dims& d, int e, int v, long long step, float lam) {
+    const uint4 r = rng_draw(d, e, (unsigned long long)step, (unsigned)v, kRngArrival);
+    return poisson_inv(lam, u01f(r.x));
+}
+
+// ---------------------------------------------------------------------------------------
+// MARL step (row a11 + a10 of SURVEY.md 8a)
+// ---------------------------------------------------------------------------------------
+template <int VP>
+__global__ void __launch_bounds__(128) k_marl_rollout(Dims d, State s, risvec_params_t p, MarlArgs a) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int e = gtid / VP, v = gtid % VP;
+    const int E = d.E, V = d.V;
+    const bool env_ok = e < E;
+    const bool act = env_ok && v < V;
+    const size_t ev = (size_t)e * V + v;
+
+    // ---- per-rollout state -> registers
+    double buf = act ? s.databuf[ev] : 0.0;
+    const double g = act ? s.gains[ev] : 0.0;
+    const int code = act ? a.partner[ev] : RISVEC_PARTNER_NONE;
+    const int ng = env_ok ? a.ngroups[e] : 1;
+    double Q = env_ok ? s.mecq[e] : 0.0;
+    const long long step0 = env_ok ? s.step_ctr[e] : 0;
+
+    const bool paired = code >= 0;
+    const bool second = paired && (code & RISVEC_PARTNER_SECOND);
+    int other = paired ? (code & (RISVEC_PARTNER_SECOND - 1)) : v;
+    other = min(max(other, 0), VP - 1);
+    const int src = (lane & ~(VP - 1)) + other;
+    const double g_o = __shfl_sync(kFull, g, src);
+    // MARL:355: the first listed user is "near" only if its gain is strictly larger
+    const bool first_near = second ? (g_o > g) : (g > g_o);
+    const bool near = paired ? (second ? !first_near : first_near) : true;
+    const float gn = (float)(g / p.noise_power);
+    const float frac = (float)(1.0 / (double)max(1, ng));  // MARL:341-342
+    const bool scheduled = code != RISVEC_PARTNER_NONE;
+
+    // ---- constants
+    const float ps = (float)p.power_scale, Pmax = (float)p.P_max;
+    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
+    const float c_thr = (float)(p.bandwidth * 1000.0);
+    double floor_d = p.cpu_share_floor;
+    if (!isfinite(floor_d)) floor_d = 0.10;
+    floor_d = fmax(0.0, fmin(floor_d, 0.95));
+    const float floor_f = (float)floor_d;
+    const double Cpb = p.cycles_per_bit;
+    const double kbit2cyc_den = Cpb * 1000.0;
+    const double edge_cap = p.f_edge_max * p.time_fast;
+    const float inv_fedge = (float)(1.0 / (p.f_edge_max + 1e-12));
+    const float inv_tf = (float)(1.0 / p.time_fast);
+    const float wd = (float)p.w_d, we = (float)p.w_e, pen = (float)p.qos_penalty, clipv = (float)p.reward_clip;
+    const float Rmin = (float)p.R_min_bpsHz, Dmax = (float)p.D_max_s;
+    const float invV = 1.0f / (float)V;
+    const float lam = (float)p.rate;
+
+    float o_rate = 0.f, o_dt = 0.f, o_dp = 0.f, o_rew = 0.f, o_glob = 0.f, o_overp = 0.f;
+    int o_arr = 0;
+
+    for (int t = 0; t < a.T; ++t) {
+        const size_t tev = ((size_t)t * E + e) * V + v;
+        const size_t ta = ((size_t)t * E + e) * 2 * V + v;
+        const float a0 = act ? a.action[ta] : 0.f;
+        const float a1 = act ? a.action[ta + V] : 0.f;
+        int arr = 0;
+        if (act) arr = a.arrivals != nullptr ? a.arrivals[tev] : draw_arrival(d, e, v, step0 + t, lam);
+
+        // power projection (MARL:555-561)
+        float p0 = fmaxf(a0, 0.f) * ps, p1 = fmaxf(a1, 0.f) * ps;
+        const float sm = p0 + p1;
+        if (sm > 1.0f) {
+            const float den = sm + 1e-12f;
+            p0 = p0 / den;
+            p1 = p1 / den;
+        }
+        const float P0 = p0 * Pmax, P1 = p1 * Pmax;
+        const float P0_o = __shfl_sync(kFull, P0, src);
+
+        // NOMA / OMA rate (MARL:339-370); log2(1+x) as log1p(x)/ln2 keeps tiny far-user SINRs
+        const float sig = P0 * gn;
+        const float sinr = near ? sig : sig / (P0_o * gn + 1.0f);
+        const float rate = scheduled ? frac * (log1pf(sinr) * 1.44269504088896341f) : 0.f;
+        const float data_t = rate * c_dt;
+
+        // local CPU (MARL:572-592) -- float64 with the reference's operation order so that the
+        // rounding residues of DataBuf - data_p (which min/max select) are reproduced
+        const float share = fmaxf(fminf(fmaxf(a1, 0.f), 1.f), floor_f);
+        const double f_local = __dmul_rn((double)share, p.f_local_max);
+        const double backlog_kbit = buf;
+        const double backlog_cyc = __dmul_rn(__dmul_rn(backlog_kbit, 1000.0), Cpb);
+        const double cap = __dmul_rn(f_local, p.time_fast);
+        const double used = fmin(cap, backlog_cyc);
+        const double local_done = __ddiv_rn(used, kbit2cyc_den);
+        const double remaining = fmax(0.0, __dsub_rn(backlog_kbit, local_done));
+        const double off = fmin((double)data_t, remaining);  // MARL:595-596
+        const float thr = rate * c_thr;
+        const float off_f = (float)off;
+        const float t_tx = off_f / (thr + 1e-12f);  // MARL:599-601
+
+        // MEC FCFS queue, one per env (MARL:604-610)
+        const double edge_in = __dmul_rn(__dmul_rn(off, 1000.0), Cpb);
+        const double edge_sum = seg_sum<VP>(edge_in);
+        const double q_before = Q;
+        Q = Q + edge_sum;
+        const double served = fmin(edge_cap, Q);
+        Q = Q - served;
+
+        buf = fmax(0.0, __dsub_rn(buf, __dadd_rn(local_done, off)));  // MARL:617-618
+
+        // delays (MARL:622-633), energy (MARL:659-661)
+        const float f_local_f = (float)f_local;
+        const float d_local = (float)fmax(0.0, backlog_cyc - edge_in) / (f_local_f + 1e-12f);
+        const float edge_in_f = (float)edge_in;
+        const float sh = edge_in_f / (float)(edge_sum + 1e-12);
+        const float d_eq = sh * ((float)q_before * inv_fedge);
+        const float d_ec = edge_in_f * inv_fedge;
+        const float delay = ((d_local + t_tx) + d_eq) + d_ec;
+        const float E_tx = P0 * t_tx;
+        const float E_loc = (float)(p.k * f_local * f_local) * (float)used;
+        const float energy = E_tx + E_loc;
+
+        // QoS penalty and reward (MARL:669-703)
+        const bool viol = p.qos_enable && ((rate < Rmin) || (delay > Dmax));
+        float rew = -(wd * delay + we * energy) - (viol ? pen : 0.f);
+        rew = fminf(fmaxf(rew, -clipv), clipv);
+        const float glob = seg_sum<VP>(act ? rew : 0.f) * invV;  // MARL:721
+        const float overp = fmaxf(0.f, (P0 + P1) - Pmax);        // MARL:727-729
+
+        // arrivals (MARL:717-719): DataBuf += (data_r * time_fast) * 1000
+        buf = __dadd_rn(buf, __dmul_rn(__dmul_rn((double)arr, p.time_fast), 1000.0));
+
+        const bool last = (t == a.T - 1);
+        if (a.out.stats != nullptr || a.out.last_power != nullptr || last) {
+            // last_* scalars (MARL:612-614,636-656,677,706-711)
+            const float m_delay = seg_sum<VP>(act ? delay : 0.f) * invV;
+            const float m_energy = seg_sum<VP>(act ? energy : 0.f) * invV;
+            const float m_dl = seg_sum<VP>(act ? d_local : 0.f) * invV;
+            const float m_dq = seg_sum<VP>(act ? d_eq : 0.f) * invV;
+            const float m_dc = seg_sum<VP>(act ? d_ec : 0.f) * invV;
+            const float m_ttx = seg_sum<VP>(act ? t_tx : 0.f) * invV;
+            const float m_back = seg_sum<VP>(act ? (float)backlog_kbit : 0.f) * invV;
+            const float util = (float)(used / (cap + 1e-12));
+            const float m_util = seg_sum<VP>(act ? util : 0.f) * invV;
+            const float m_viol = seg_sum<VP>((act && viol) ? 1.f : 0.f) * invV;
+            const float s_off = seg_sum<VP>(act ? off_f : 0.f);
+            const float s_loc = seg_sum<VP>(act ? (float)local_done : 0.f);
+            const float mec_util = (float)(served / (edge_cap + 1e-12));
+            const float q_f = (float)Q;
+            auto stat_of = [&](int col) -> float {
+                switch (col) {
+                    case RISVEC_S_DELAY_MEAN: return m_delay;
+                    case RISVEC_S_ENERGY_MEAN: return m_energy;
+                    case RISVEC_S_DELAY_LOCAL_MEAN: return m_dl;
+                    case RISVEC_S_DELAY_EDGE_Q_MEAN: return m_dq;
+                    case RISVEC_S_DELAY_EDGE_C_MEAN: return m_dc;
+                    case RISVEC_S_T_TX_MEAN: return m_ttx;
+                    case RISVEC_S_BACKLOG_KBIT_MEAN: return m_back;
+                    case RISVEC_S_MEC_UTILIZATION: return mec_util;
+                    case RISVEC_S_LOCAL_UTIL_MEAN: return m_util;
+                    case RISVEC_S_QOS_VIOLATION: return m_viol;
+                    case RISVEC_S_OFF_KBIT_SUM: return s_off;
+                    case RISVEC_S_LOCAL_KBIT_SUM: return s_loc;
+                    case RISVEC_S_MEC_QUEUE_CYCLES: return q_f;
+                    default: return 0.f;
+                }
+            };
+            // lane v of the env writes stat columns v, v + VP, ... (coalesced rows of NSTAT floats)
+            if (env_ok) {
+                for (int col = v; col < RISVEC_NSTAT; col += VP) {
+                    const float val = stat_of(col);
+                    if (a.out.stats != nullptr) a.out.stats[((size_t)t * E + e) * RISVEC_NSTAT + col] = val;
+                    if (last) s.stats[(size_t)e * RISVEC_NSTAT + col] = val;
+                }
+            }
+            if (act) {  // last_power_W = [E_tx, E_loc] / time_fast (MARL:664-666)
+                const float ptx = E_tx * inv_tf, ploc = E_loc * inv_tf;
+                if (a.out.last_power != nullptr) {
+                    a.out.last_power[ta] = ptx;
+                    a.out.last_power[ta + V] = ploc;
+                }
+                if (last) {
+                    s.last_power[(size_t)e * 2 * V + v] = ptx;
+                    s.last_power[(size_t)e * 2 * V + V + v] = ploc;
+                }
+            }
+        }
+        if (act) {
+            if (a.out.reward_user != nullptr) a.out.reward_user[tev] = rew;
+            if (a.out.DataBuf != nullptr) a.out.DataBuf[tev] = (float)buf;
+            if (a.out.data_t != nullptr) a.out.data_t[tev] = data_t;
+            if (a.out.data_p != nullptr) a.out.data_p[tev] = (float)local_done;
+            if (a.out.rate != nullptr) a.out.rate[tev] = rate;
+            if (a.out.over_power != nullptr) a.out.over_power[tev] = overp;
+            if (v == 0 && a.out.reward != nullptr) a.out.reward[(size_t)t * E + e] = glob;
+        }
+        o_rate = rate; o_dt = data_t; o_dp = (float)local_done; o_rew = rew; o_glob = glob; o_overp = overp;
+        o_arr = arr;
+    }
+
+    // ---- registers -> state
+    if (act && a.T > 0) {
+        s.databuf[ev] = buf;
+        s.rate[ev] = o_rate;
+        s.data_t[ev] = o_dt;
+        s.data_p[ev] = o_dp;
+        s.reward_user[ev] = o_rew;
+        s.over_power[ev] = o_overp;
+        s.data_r[ev] = o_arr;
+        if (v == 0) {
+            s.mecq[e] = Q;
+            s.reward[e] = o_glob;
+            s.step_ctr[e] = step0 + a.T;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// SARL step (row a12): per step the V x M cascaded RIS reduction
+//   S_v = sum_m exp(j*phase_m) * phasor(v, m),  rate_v = ln(1 + P0_v * amp_v * |S_v|^2 / sigma^2)
+// The geometry phasor table (depends only on positions) is built once per launch in float64
+// and kept in registers: lane (env, v) of warp w holds elements [w*slice, (w+1)*slice).
+// WPE warps share one env group and combine their partial sums through shared memory.
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ void phasor_f32(double x, float* re, float* im) {
+    double s64, c64;
+    sincospi(x, &s64, &c64);
+    *re = (float)c64;
+    *im = (float)s64;
+}
+
+template <int VP, int MPL, int WPE>
+__global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
+    constexpr int EPW = 32 / VP;  // envs per warp (= per block)
+    extern __shared__ float2 sarl_smem[];
+    const int E = d.E, V = d.V, M = d.M;
+    const int MS = M + 2;  // padded env stride of the theta table (bank spread)
+    float2* th = sarl_smem;                // [EPW][MS]
+    float2* part = sarl_smem + EPW * MS;   // [WPE][32] (WPE > 1 only)
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int el = lane / VP, v = lane % VP;
+    const int e0 = blockIdx.x * EPW;
+    const int e = e0 + el;
+    const bool env_ok = e < E;
+    const bool act = env_ok && v < V;
+    const size_t ev = (size_t)e * V + v;
+    const int slice = (M + WPE - 1) / WPE;
+    const int m0 = w * slice;
+    const int m1 = min(M, m0 + slice);
+
+    // ---- geometry phasor table -> registers (float64 argument reduction, float32 storage)
+    float wr[MPL], wi[MPL];
+    {
+        const double delta = act ? d.angle_BR - s.angle[ev] : 0.0;
+#pragma unroll
+        for (int i = 0; i < MPL; ++i) {
+            const int m = m0 + i;
+            float re = 0.f, im = 0.f;
+            if (act && m < m1) phasor_f32((double)m * delta, &re, &im);
+            wr[i] = re;
+            wi[i] = im;
+        }
+    }
+    const bool cphase = (w == 0);
+    double buf = (act && cphase) ? s.databuf[ev] : 0.0;
+    const float coef = act ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
+    const long long step0 = env_ok ? s.step_ctr[e] : 0;
+
+    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
+    const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);       // SARL:331
+    const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));             // SARL:318-319
+    const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
+    const float invV = 1.0f / (float)V;
+    const float lam = (float)p.rate;
+    const int n_env_here = min(EPW, E - e0);
+
+    float o_rate = 0.f, o_dt = 0.f, o_dp = 0.f, o_overp = 0.f, o_overd = 0.f, o_rew = 0.f;
+    int o_arr = 0;
+
+    for (int t = 0; t < a.T; ++t) {
+        // (1) theta_m = exp(j*phase_m) for the block's envs (SARL:125-131); the EPW rows of
+        //     phase[t] are contiguous in HBM
+        const float* ph_t = a.phase + ((size_t)t * E + e0) * M;
+        const bool last = (t == a.T - 1);
+        for (int idx = threadIdx.x; idx < n_env_here * M; idx += 32 * WPE) {
+            const float ph = ph_t[idx];
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            const int el2 = idx / M, m = idx - el2 * M;
+            th[el2 * MS + m] = make_float2(cs, sn);
+            if (last) s.phase_real[(size_t)e0 * M + idx] = ph;
+        }
+        if (WPE > 1) __syncthreads(); else __syncwarp();
+
+        // (2) cascaded reduction over this warp's element slice
+        float sr = 0.f, si = 0.f;
+        const float2* th_e = th + el * MS + m0;
+#pragma unroll
+        for (int i = 0; i < MPL; ++i) {
+            if (m0 + i < m1) {
+                const float2 tq = th_e[i];
+                sr = fmaf(tq.x, wr[i], sr);
+                sr = fmaf(-tq.y, wi[i], sr);
+                si = fmaf(tq.x, wi[i], si);
+                si = fmaf(tq.y, wr[i], si);
+            }
+        }
+        if (WPE > 1) {
+            part[w * 32 + lane] = make_float2(sr, si);
+            __syncthreads();
+            if (cphase) {
+                sr = 0.f; si = 0.f;
+#pragma unroll
+                for (int k = 0; k < WPE; ++k) {
+                    const float2 q = part[k * 32 + lane];
+                    sr += q.x; si += q.y;
+                }
+            }
+        } else {
+            __syncwarp();
+        }
+
+        // (3) per-vehicle queue update and reward (SARL:327-358), first warp of the block
+        if (cphase) {
+            const size_t tev = ((size_t)t * E + e) * V + v;
+            const size_t ta = ((size_t)t * E + e) * 2 * V + v;
+            const float a0 = act ? a.action[ta] : 0.f;
+            const float a1 = act ? a.action[ta + V] : 0.f;
+            int arr = 0;
+            if (act) arr = a.arrivals != nullptr ? a.arrivals[tev] : draw_arrival(d, e, v, step0 + t, lam);
+
+            const float g2 = sr * sr + si * si;
+            const float rate = log1pf(a0 * (coef * g2));  // natural log, SARL:159
+            const float data_t = rate * c_dt;
+            const float data_p = cbrtf(a1) * c_dp;
+            double nb = buf - ((double)data_t + (double)data_p);  // SARL:334
+            float overp = 0.f, overd = 0.f;
+            if (nb < 0.0) {  // SARL:336-339
+                const float b = (float)fmax(0.0, nb + (double)data_p) * c_rev;
+                overp = a1 - b * b * b;
+                overd = (float)(-nb);
+                nb = 0.0;
+            }
+            const float nbf = (float)nb;
+            const float base = -(t1 * (a0 + a1)) - (t2 * nbf);
+            const float ru = (nb > 0.0) ? base - pen1 : ((overd > 2.0f) ? base - pen2 : base);  // SARL:343-352
+            const float rew = seg_sum<VP>(act ? ru : 0.f) * invV;
+            buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, p.time_fast), 1000.0));  // SARL:354-356
+
+            if (act) {
+                if (a.out.DataBuf != nullptr) a.out.DataBuf[tev] = (float)buf;
+                if (a.out.data_t != nullptr) a.out.data_t[tev] = data_t;
+                if (a.out.data_p != nullptr) a.out.data_p[tev] = data_p;
+                if (a.out.over_power != nullptr) a.out.over_power[tev] = overp;
+                if (a.out.over_data != nullptr) a.out.over_data[tev] = overd;
+                if (a.out.rate != nullptr) a.out.rate[tev] = rate;
+                if (v == 0 && a.out.reward != nullptr) a.out.reward[(size_t)t * E + e] = rew;
+            }
+            o_rate = rate; o_dt = data_t; o_dp = data_p; o_overp = overp; o_overd = overd; o_rew = rew; o_arr = arr;
+        }
+    }
+
+    if (cphase && act && a.T > 0) {
+        s.databuf[ev] = buf;
+        s.rate[ev] = o_rate;
+        s.data_t[ev] = o_dt;
+        s.data_p[ev] = o_dp;
+        s.over_power[ev] = o_overp;
+        s.over_data[ev] = o_overd;
+        s.data_r[ev] = o_arr;
+        if (v == 0) {
+            s.reward[e] = o_rew;
+            s.step_ctr[e] = step0 + a.T;
+        }
+    }
+}
+
+}  // namespace risvec

@@ -84,6 +84,8 @@ class OracleBackend:
                    over_power=over_p, rate=e.vehicle_rate, last_power_W=e.last["power_W"])
         for k in MARL_LAST:
             out["last_" + k] = e.last[k]
+        # extras (prefix x_) feed the band-exclusion rules of tests/parity.py; not fixture keys
+        out.update(x_delay=e.last["delay"], x_edge_in_sum=e.last["edge_in_sum"], x_q_before=e.last["q_before"])
         return out
 
     def step_sarl(self, actions, phases, arrivals):
@@ -91,7 +93,7 @@ class OracleBackend:
         r, over_p = self.env.step_sarl(actions, phases)
         e = self.env
         return dict(reward=r, DataBuf=e.DataBuf, data_t=e.data_t, data_p=e.data_p, over_power=over_p,
-                    over_data=e.over_data, rate=e.vehicle_rate)
+                    over_data=e.over_data, rate=e.vehicle_rate, x_buf_pre=e.DataBuf - e.data_r)
 
 
 def replay(g, backend):

@@ -1,0 +1,72 @@
+"""CPU-side checks of the C-ABI boundary: the shared library builds for sm_100a, loads, and
+exports every symbol include/risvec.h declares; the ctypes mirror of `risvec_params_t`
+matches the C layout.  No CUDA call is made."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from ris_vec_marl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _lib.build_library()
+    return _lib.load_library()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "risvec.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(risvec_[a-z_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/risvec.h but not exported"
+        assert n in _lib.EXPORTS, f"{n} has no ctypes prototype"
+
+
+def test_abi_version_and_default_params(lib):
+    assert lib.risvec_abi_version() == 1
+    p = _lib.Params()
+    assert lib.risvec_default_params(0, C.byref(p)) == 0
+    # reference class defaults (MARL/Environment.py:70-143)
+    assert (p.bandwidth, p.P_max, p.f_local_max, p.cycles_per_bit, p.w_d, p.w_e) == (1.0, 1.0, 1e9, 500.0, 0.5, 3.0)
+    assert (p.R_min_bpsHz, p.D_max_s, p.qos_penalty, p.rate, p.qos_enable) == (0.20, 0.10, 5.0, 3.0, 1)
+    assert abs(p.noise_power - 10 ** ((-174 - 30) / 10) * 1e6) < 1e-28
+    assert list(p.up_lanes)[:4] == [200.875, 202.625, 400.875, 402.625]
+    assert list(p.down_lanes)[:4] == [197.375, 199.125, 397.375, 399.125]
+    # last member intact => the python struct has the C layout
+    assert (p.t_factor1, p.t_factor2, p.penalty1, p.penalty2) == (1.0, 0.6, 2.0, 2.0)
+
+
+def test_errors_are_reported_not_thrown(lib):
+    h = C.c_void_p()
+    rc = lib.risvec_create(None, 0, 4, 8, 40, 3, 0, 1, 0, C.byref(h))
+    assert rc == -1 and b"params" in lib.risvec_last_error()
+    p = _lib.Params()
+    lib.risvec_default_params(0, C.byref(p))
+    assert lib.risvec_create(C.byref(p), 0, 4, 64, 40, 3, 0, 1, 0, C.byref(h)) == -2  # V > 32 unsupported
+    assert lib.risvec_create(C.byref(p), 7, 4, 8, 40, 3, 0, 1, 0, C.byref(h)) == -1
+    assert lib.risvec_destroy(None) == 0
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ris_vec_marl_b200 import BatchedEnviron, RisvecLibraryError
+
+    with pytest.raises(RisvecLibraryError):
+        BatchedEnviron("marl", 4)
+    p = _lib.Params()
+    lib.risvec_default_params(0, C.byref(p))
+    h = C.c_void_p()
+    assert lib.risvec_create(C.byref(p), 0, 4, 8, 40, 3, 0, 1, 0, C.byref(h)) == -4  # RISVEC_ERR_NODEVICE

@@ -60,6 +60,16 @@ def sarl_exclusions(g, want):
     return user, user.any(axis=-1)
 
 
+def sarl_rate_atol(M):
+    """SARL recomputes the cascaded sum S_v = sum_m theta_m w_vm every step from float32 phasors:
+    2M components carrying ~6e-8 representation error each bound |S_v| to ~1e-7*sqrt(2M) and
+    the float32 accumulation adds about as much again.  Where the M phasors interfere
+    destructively (|S| << sqrt(M)) that absolute error dominates rate = ln(1 + c |S|^2), so
+    the SARL rate (and data_t = rate in kbit) gets an absolute floor growing with sqrt(M)
+    (hard part 2: "the tail needs ... an atol tied to M*ulp")."""
+    return 6e-7 * np.sqrt(M)
+
+
 def compare_replays(g, got, want, params=None):
     """`got` = CUDA replay, `want` = oracle replay (with its `step_x_*` extras); both are also
     checked against the reference fixture `g` where it holds the key."""
@@ -92,6 +102,10 @@ def compare_replays(g, got, want, params=None):
             continue
         name = k[5:]
         atol = ATOL[name]
+        if g["variant"] == "sarl" and name in ("rate", "data_t"):
+            atol = max(atol, sarl_rate_atol(g["M"]))
+        if g["variant"] == "sarl" and name in ("DataBuf", "over_data"):
+            atol = max(atol, 4 * sarl_rate_atol(g["M"]))  # accumulates a few steps of data_t error
         mask = None
         if name in per_user_masked:
             mask = user_x

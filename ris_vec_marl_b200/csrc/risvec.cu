@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -58,6 +59,7 @@ struct risvec_env {
     // device staging for the *_host entry points (grow-only)
     char* stage;
     size_t stage_bytes;
+    int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
 };
 
 namespace {
@@ -126,9 +128,20 @@ int launch_sarl_cfg(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     return check_launch(env, "k_sarl_rollout");
 }
 
+template <int MPI, int U>
+int launch_sarl_v8(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
+    const int warps = (env->dims.E + 3) / 4;
+    k_sarl_v8<MPI, U><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+    return check_launch(env, "k_sarl_v8");
+}
+
 template <int VP>
 int launch_sarl(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     const int M = env->dims.M;
+    if (VP <= 8 && M <= 40 && !env->force_generic) {  // fast path: elements split over the env's 8 lanes
+        if (a.T == 1) return M <= 16 ? launch_sarl_v8<2, 1>(env, a, st) : launch_sarl_v8<5, 1>(env, a, st);
+        return M <= 16 ? launch_sarl_v8<2, 2>(env, a, st) : launch_sarl_v8<5, 2>(env, a, st);
+    }
     // elements per lane: M / WPE, register-resident table of MPL complex floats
     if (M <= 16) return launch_sarl_cfg<VP, 16, 1>(env, a, st);
     if (M <= 40) return launch_sarl_cfg<VP, 40, 1>(env, a, st);
@@ -152,21 +165,19 @@ struct Carver {
 };
 
 __global__ void k_shard_stats(Dims d, State s, double* out) {
-    // one block; column c of the stats (and the reward as column NSTAT) summed over envs
+    // block c sums column c of the stats over the shard's envs (column NSTAT = global reward)
     __shared__ double red[32];
-    for (int c = 0; c <= RISVEC_NSTAT; ++c) {
-        double acc = 0.0;
-        for (int e = threadIdx.x; e < d.E; e += blockDim.x)
-            acc += (c < RISVEC_NSTAT) ? (double)s.stats[(size_t)e * RISVEC_NSTAT + c] : (double)s.reward[e];
-        acc = seg_sum<32>(acc);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-            v = seg_sum<32>(v);
-            if (threadIdx.x == 0) out[c] = v;
-        }
-        __syncthreads();
+    const int c = blockIdx.x;
+    double acc = 0.0;
+    for (int e = threadIdx.x; e < d.E; e += blockDim.x)
+        acc += (c < RISVEC_NSTAT) ? (double)s.stats[(size_t)e * RISVEC_NSTAT + c] : (double)s.reward[e];
+    acc = seg_sum<32>(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        v = seg_sum<32>(v);
+        if (threadIdx.x == 0) out[c] = v;
     }
 }
 
@@ -236,6 +247,10 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
     memset(env, 0, sizeof(*env));
     env->device = device;
     env->params = *params;
+    {
+        const char* fg = getenv("RISVEC_FORCE_GENERIC");
+        env->force_generic = (fg != nullptr && fg[0] == '1');
+    }
     Dims& d = env->dims;
     d.E = E; d.V = V; d.M = M; d.ncand = 1 << control_bit; d.variant = variant;
     d.seed = seed; d.env_base = env_index_base;
@@ -511,7 +526,7 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
 int risvec_shard_stats(risvec_env_t* env, double* out, void* stream) {
     if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(env->device));
-    k_shard_stats<<<1, 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
+    k_shard_stats<<<RISVEC_NSTAT + 1, 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
     return check_launch(env, "k_shard_stats");
 }
 

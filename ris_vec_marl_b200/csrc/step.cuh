@@ -406,4 +406,213 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
     }
 }
 
+// =========================================================================================
+// SARL fast path for V <= 8, M <= 8 * MPI (BASELINE configs 1-2: V = 8, M = 40, MPI = 5)
+// =========================================================================================
+// One warp = 4 envs; lane = (env el, part).  For the cascaded reduction the 8 lanes of an env
+// split the ELEMENT axis: lane `part` owns elements m = part + 8 i (i < MPI), evaluates
+// exp(j*phase_m) for them once, and multiplies them into the partial sums of ALL 8 vehicles
+// (geometry phasors of its elements x 8 vehicles sit in registers as packed float2 pairs so
+// the MACs issue as FFMA2).  A 3-stage butterfly (reduce-scatter over lanes xor 4, 2, 1) then
+// leaves the total S_v on lane part = v, which runs the per-vehicle queue update.
+// No shared memory, no block barrier.  U consecutive steps are processed together: their
+// state-independent parts (phasors, reduction, rate, data_t, data_p) are independent
+// instruction streams the scheduler interleaves; only the DataBuf recursion is sequential.
+// Inputs for the next U steps are prefetched into registers while the current ones compute.
+
+// sin/cos of a float32 angle in radians; |x| < ~1e4 (RIS phases live in [0, 2*pi]).
+// Cody-Waite reduction to [-pi/4, pi/4] + Cephes minimax polynomials (<= 1 ulp there).
+__device__ __forceinline__ void sincos_fast(float x, float* sn, float* cs) {
+    const float kf = rintf(x * 0.63661977236758134f);
+    float r = fmaf(kf, -1.5707963705062866f, x);
+    r = fmaf(kf, 4.3711390001862426e-8f, r);
+    const int q = (int)kf;
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    const float s0 = fmaf(ps * r2, r, r);
+    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, r2, 4.166664568298827e-2f);
+    const float c0 = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.0f));
+    const bool swap = q & 1;
+    const float s1 = swap ? c0 : s0, c1 = swap ? s0 : c0;
+    *sn = (q & 2) ? -s1 : s1;
+    *cs = ((q + 1) & 2) ? -c1 : c1;
+}
+
+__device__ __forceinline__ float2 shfl_xor2(float2 x, int o) {
+    return make_float2(__shfl_xor_sync(kFull, x.x, o), __shfl_xor_sync(kFull, x.y, o));
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+
+template <int MPI>
+struct SarlStepIn {
+    float ph[MPI];
+    float a0, a1;
+    int arr;
+};
+
+template <int MPI, int U>
+__global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t p, SarlArgs a) {
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, el = lane >> 3, part = lane & 7;
+    const int E = d.E, V = d.V, M = d.M, T = a.T;
+    if (warp * 4 >= E) return;
+    const int e = warp * 4 + el, v = part;
+    const bool env_ok = e < E;
+    const bool act = env_ok && v < V;
+    const size_t ev = (size_t)e * V + v;
+
+    // ---- geometry phasors of my elements for all 8 vehicles -> registers
+    float2 WX[MPI][4], WY[MPI][4];
+    {
+        const double my_delta = act ? d.angle_BR - s.angle[ev] : 0.0;
+#pragma unroll
+        for (int v2 = 0; v2 < 8; ++v2) {
+            const double dv = __shfl_sync(kFull, my_delta, (lane & ~7) + v2);
+            const bool ok2 = env_ok && v2 < V;
+#pragma unroll
+            for (int i = 0; i < MPI; ++i) {
+                const int m = part + 8 * i;
+                float re = 0.f, im = 0.f;
+                if (ok2 && m < M) phasor_f32((double)m * dv, &re, &im);
+                if (v2 & 1) { WX[i][v2 >> 1].y = re; WY[i][v2 >> 1].y = im; }
+                else        { WX[i][v2 >> 1].x = re; WY[i][v2 >> 1].x = im; }
+            }
+        }
+    }
+    double buf = act ? s.databuf[ev] : 0.0;
+    const float coef = act ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
+    const long long step0 = env_ok ? s.step_ctr[e] : 0;
+    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
+    const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);  // SARL:331
+    const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));        // SARL:318-319
+    const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
+    const float invV = 1.0f / (float)V;
+    const float lam = (float)p.rate;
+    const bool b2 = part & 4, b1 = part & 2, b0 = part & 1;
+
+    auto load_in = [&](SarlStepIn<MPI>& in, int t) {
+        const float* ph_t = a.phase + ((size_t)t * E + e) * M;
+#pragma unroll
+        for (int i = 0; i < MPI; ++i) {
+            const int m = part + 8 * i;
+            in.ph[i] = (env_ok && m < M) ? __ldg(ph_t + m) : 0.f;
+        }
+        const size_t ta = ((size_t)t * E + e) * 2 * V + v;
+        in.a0 = act ? __ldg(a.action + ta) : 0.f;
+        in.a1 = act ? __ldg(a.action + ta + V) : 0.f;
+        in.arr = (act && a.arrivals != nullptr) ? __ldg(a.arrivals + ((size_t)t * E + e) * V + v) : 0;
+    };
+
+    SarlStepIn<MPI> cur[U], nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (u < T) load_in(cur[u], u);
+
+    float o_rate = 0.f, o_dt = 0.f, o_dp = 0.f, o_overp = 0.f, o_overd = 0.f, o_rew = 0.f;
+    int o_arr = 0;
+
+    for (int t0 = 0; t0 < T; t0 += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (t0 + U + u < T) load_in(nxt[u], t0 + U + u);
+
+        // ---- state-independent part of the U steps
+        float rate[U], data_t[U], data_p[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float2 RE[4], IM[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) RE[k] = IM[k] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < MPI; ++i) {
+                float sn, cs;
+                sincos_fast(cur[u].ph[i], &sn, &cs);  // theta_m = exp(j*phase_m), SARL:125-131
+                const float2 TX = make_float2(cs, cs), TY = make_float2(sn, sn), NTY = make_float2(-sn, -sn);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // theta_m * w_vm for the vehicle pair (2k, 2k+1)
+                    RE[k] = __ffma2_rn(TX, WX[i][k], RE[k]);
+                    RE[k] = __ffma2_rn(NTY, WY[i][k], RE[k]);
+                    IM[k] = __ffma2_rn(TX, WY[i][k], IM[k]);
+                    IM[k] = __ffma2_rn(TY, WX[i][k], IM[k]);
+                }
+            }
+            // reduce-scatter over the env's 8 lanes: lane `part` ends with vehicle v = part
+            float2 r0 = b2 ? RE[2] : RE[0], r1 = b2 ? RE[3] : RE[1];
+            float2 i0 = b2 ? IM[2] : IM[0], i1 = b2 ? IM[3] : IM[1];
+            r0 = add2(r0, shfl_xor2(b2 ? RE[0] : RE[2], 4)); r1 = add2(r1, shfl_xor2(b2 ? RE[1] : RE[3], 4));
+            i0 = add2(i0, shfl_xor2(b2 ? IM[0] : IM[2], 4)); i1 = add2(i1, shfl_xor2(b2 ? IM[1] : IM[3], 4));
+            float2 r = add2(b1 ? r1 : r0, shfl_xor2(b1 ? r0 : r1, 2));
+            float2 im = add2(b1 ? i1 : i0, shfl_xor2(b1 ? i0 : i1, 2));
+            const float sr = (b0 ? r.y : r.x) + __shfl_xor_sync(kFull, b0 ? r.x : r.y, 1);
+            const float si = (b0 ? im.y : im.x) + __shfl_xor_sync(kFull, b0 ? im.x : im.y, 1);
+
+            const float g2 = sr * sr + si * si;
+            rate[u] = log1pf(cur[u].a0 * (coef * g2));  // natural log, SARL:159
+            data_t[u] = rate[u] * c_dt;
+            data_p[u] = cbrtf(cur[u].a1) * c_dp;
+        }
+
+        // ---- DataBuf recursion and reward, sequential over the U steps (SARL:333-358)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u;
+            if (t < T) {
+                const float a0 = cur[u].a0, a1 = cur[u].a1;
+                int arr = cur[u].arr;
+                if (act && a.arrivals == nullptr) arr = draw_arrival(d, e, v, step0 + t, lam);
+                double nb = buf - ((double)data_t[u] + (double)data_p[u]);
+                float overp = 0.f, overd = 0.f;
+                if (nb < 0.0) {
+                    const float b = (float)fmax(0.0, nb + (double)data_p[u]) * c_rev;
+                    overp = a1 - b * b * b;
+                    overd = (float)(-nb);
+                    nb = 0.0;
+                }
+                const float nbf = (float)nb;
+                const float base = -(t1 * (a0 + a1)) - (t2 * nbf);
+                const float ru = (nb > 0.0) ? base - pen1 : ((overd > 2.0f) ? base - pen2 : base);
+                const float rew = seg_sum<8>(act ? ru : 0.f) * invV;
+                buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, p.time_fast), 1000.0));
+                if (act) {
+                    const size_t tev = ((size_t)t * E + e) * V + v;
+                    if (a.out.DataBuf != nullptr) a.out.DataBuf[tev] = (float)buf;
+                    if (a.out.data_t != nullptr) a.out.data_t[tev] = data_t[u];
+                    if (a.out.data_p != nullptr) a.out.data_p[tev] = data_p[u];
+                    if (a.out.over_power != nullptr) a.out.over_power[tev] = overp;
+                    if (a.out.over_data != nullptr) a.out.over_data[tev] = overd;
+                    if (a.out.rate != nullptr) a.out.rate[tev] = rate[u];
+                    if (v == 0 && a.out.reward != nullptr) a.out.reward[(size_t)t * E + e] = rew;
+                }
+                if (t == T - 1) {
+                    o_rate = rate[u]; o_dt = data_t[u]; o_dp = data_p[u]; o_overp = overp; o_overd = overd;
+                    o_rew = rew; o_arr = arr;
+#pragma unroll
+                    for (int i = 0; i < MPI; ++i) {  // elements_phase_shift_real = action_phase
+                        const int m = part + 8 * i;
+                        if (env_ok && m < M) s.phase_real[(size_t)e * M + m] = cur[u].ph[i];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+    }
+
+    if (act && T > 0) {
+        s.databuf[ev] = buf;
+        s.rate[ev] = o_rate;
+        s.data_t[ev] = o_dt;
+        s.data_p[ev] = o_dp;
+        s.over_power[ev] = o_overp;
+        s.over_data[ev] = o_overd;
+        s.data_r[ev] = o_arr;
+        if (v == 0) {
+            s.reward[e] = o_rew;
+            s.step_ctr[e] = step0 + T;
+        }
+    }
+}
+
 }  // namespace risvec

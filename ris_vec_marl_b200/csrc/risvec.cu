@@ -128,20 +128,27 @@ int launch_sarl_cfg(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     return check_launch(env, "k_sarl_rollout");
 }
 
-template <int MPI, int U>
+template <int MPI>
 int launch_sarl_v8(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     const int warps = (env->dims.E + 3) / 4;
-    k_sarl_v8<MPI, U><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+    const bool mfull = env->dims.M == 8 * MPI;
+    const risvec_sarl_out_t& o = a.out;
+    const bool full = a.arrivals && o.reward && o.DataBuf && o.data_t && o.data_p && o.over_power && o.over_data &&
+                      o.rate;
+    if (mfull && full)
+        k_sarl_v8<MPI, true, true><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+    else if (mfull)
+        k_sarl_v8<MPI, true, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+    else
+        k_sarl_v8<MPI, false, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
     return check_launch(env, "k_sarl_v8");
 }
 
 template <int VP>
 int launch_sarl(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     const int M = env->dims.M;
-    if (VP <= 8 && M <= 40 && !env->force_generic) {  // fast path: elements split over the env's 8 lanes
-        if (a.T == 1) return M <= 16 ? launch_sarl_v8<2, 1>(env, a, st) : launch_sarl_v8<5, 1>(env, a, st);
-        return M <= 16 ? launch_sarl_v8<2, 2>(env, a, st) : launch_sarl_v8<5, 2>(env, a, st);
-    }
+    if (VP <= 8 && M <= 40 && !env->force_generic)  // fast path: elements split over the env's 8 lanes
+        return M <= 16 ? launch_sarl_v8<2>(env, a, st) : launch_sarl_v8<5>(env, a, st);
     // elements per lane: M / WPE, register-resident table of MPL complex floats
     if (M <= 16) return launch_sarl_cfg<VP, 16, 1>(env, a, st);
     if (M <= 40) return launch_sarl_cfg<VP, 40, 1>(env, a, st);

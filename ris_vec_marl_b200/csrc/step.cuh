@@ -411,39 +411,48 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
 // =========================================================================================
 // One warp = 4 envs; lane = (env el, part).  For the cascaded reduction the 8 lanes of an env
 // split the ELEMENT axis: lane `part` owns elements m = part + 8 i (i < MPI), evaluates
-// exp(j*phase_m) for them once, and multiplies them into the partial sums of ALL 8 vehicles
-// (geometry phasors of its elements x 8 vehicles sit in registers as packed float2 pairs so
-// the MACs issue as FFMA2).  A 3-stage butterfly (reduce-scatter over lanes xor 4, 2, 1) then
-// leaves the total S_v on lane part = v, which runs the per-vehicle queue update.
-// No shared memory, no block barrier.  U consecutive steps are processed together: their
+// exp(j*phase_m) for them once, and multiplies them into the partial sums of ALL 8 vehicles.
+// The geometry phasors of its elements x 8 vehicles sit in registers as packed float2 pairs
+// (FFMA2 on Blackwell), stored in the lane-dependent vehicle order slot = v ^ part so that the
+// 3-stage reduce-scatter over lanes xor 4, 2, 1 needs no selects: a lane always keeps the low
+// half of its slots and sends the high half, and ends with the total S_v of vehicle v = part,
+// for which it then runs the per-vehicle queue update.
+// No shared memory, no block barrier.  Two consecutive steps are processed together: their
 // state-independent parts (phasors, reduction, rate, data_t, data_p) are independent
-// instruction streams the scheduler interleaves; only the DataBuf recursion is sequential.
-// Inputs for the next U steps are prefetched into registers while the current ones compute.
+// instruction streams -- the sin/cos evaluation is packed across the two steps (fp32x2) --
+// and only the DataBuf recursion is sequential.  Inputs of the next two steps are prefetched
+// into registers while the current ones compute.
 
-// sin/cos of a float32 angle in radians; |x| < ~1e4 (RIS phases live in [0, 2*pi]).
-// Cody-Waite reduction to [-pi/4, pi/4] + Cephes minimax polynomials (<= 1 ulp there).
-__device__ __forceinline__ void sincos_fast(float x, float* sn, float* cs) {
-    const float kf = rintf(x * 0.63661977236758134f);
-    float r = fmaf(kf, -1.5707963705062866f, x);
-    r = fmaf(kf, 4.3711390001862426e-8f, r);
-    const int q = (int)kf;
-    const float r2 = r * r;
-    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
-    ps = fmaf(ps, r2, -1.6666654611e-1f);
-    const float s0 = fmaf(ps * r2, r, r);
-    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
-    pc = fmaf(pc, r2, 4.166664568298827e-2f);
-    const float c0 = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.0f));
-    const bool swap = q & 1;
-    const float s1 = swap ? c0 : s0, c1 = swap ? s0 : c0;
-    *sn = (q & 2) ? -s1 : s1;
-    *cs = ((q + 1) & 2) ? -c1 : c1;
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
+// sin/cos of two float32 angles (radians, |x| < ~1e4; RIS phases live in [0, 2*pi]) in packed
+// fp32x2 arithmetic: Cody-Waite reduction to [-pi/4, pi/4] by quadrants, Cephes minimax
+// polynomials (<= 1 ulp there), quadrant fix-up with integer sign flips.
+__device__ __forceinline__ void sincos_fast2(float2 x, float2* sn, float2* cs) {
+    const float2 t = __ffma2_rn(x, f2(0.63661977236758134f), f2(12582912.f));  // 1.5 * 2^23: rint
+    const float2 kf = __fadd2_rn(t, f2(-12582912.f));
+    float2 r = __ffma2_rn(kf, f2(-1.5707963705062866f), x);
+    r = __ffma2_rn(kf, f2(4.3711390001862426e-8f), r);
+    const float2 r2 = __fmul2_rn(r, r);
+    float2 ps = __ffma2_rn(r2, f2(-1.9515295891e-4f), f2(8.3321608736e-3f));
+    ps = __ffma2_rn(ps, r2, f2(-1.6666654611e-1f));
+    const float2 s0 = __ffma2_rn(__fmul2_rn(ps, r2), r, r);
+    float2 pc = __ffma2_rn(r2, f2(2.443315711809948e-5f), f2(-1.388731625493765e-3f));
+    pc = __ffma2_rn(pc, r2, f2(4.166664568298827e-2f));
+    const float2 c0 = __ffma2_rn(__fmul2_rn(pc, r2), r2, __ffma2_rn(r2, f2(-0.5f), f2(1.0f)));
+    // the low mantissa bits of t hold the quadrant k mod 4
+    const int qa = __float_as_int(t.x), qb = __float_as_int(t.y);
+    const float sa = (qa & 1) ? c0.x : s0.x, ca = (qa & 1) ? s0.x : c0.x;
+    const float sb = (qb & 1) ? c0.y : s0.y, cb = (qb & 1) ? s0.y : c0.y;
+    sn->x = __int_as_float(__float_as_int(sa) ^ ((qa << 30) & 0x80000000));
+    cs->x = __int_as_float(__float_as_int(ca) ^ (((qa + 1) << 30) & 0x80000000));
+    sn->y = __int_as_float(__float_as_int(sb) ^ ((qb << 30) & 0x80000000));
+    cs->y = __int_as_float(__float_as_int(cb) ^ (((qb + 1) << 30) & 0x80000000));
 }
 
 __device__ __forceinline__ float2 shfl_xor2(float2 x, int o) {
     return make_float2(__shfl_xor_sync(kFull, x.x, o), __shfl_xor_sync(kFull, x.y, o));
 }
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 
 template <int MPI>
 struct SarlStepIn {
@@ -452,23 +461,47 @@ struct SarlStepIn {
     int arr;
 };
 
-template <int MPI, int U>
+// theta_m * w[slot] accumulated for the 4 slot pairs of one element
+__device__ __forceinline__ void sarl_mac(float cs, float sn, const float2 (&WX)[4], const float2 (&WY)[4],
+                                         float2 (&RE)[4], float2 (&IM)[4]) {
+    const float2 TX = f2(cs), TY = f2(sn), NTY = f2(__int_as_float(__float_as_int(sn) ^ 0x80000000));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        RE[k] = __ffma2_rn(TX, WX[k], RE[k]);
+        RE[k] = __ffma2_rn(NTY, WY[k], RE[k]);
+        IM[k] = __ffma2_rn(TX, WY[k], IM[k]);
+        IM[k] = __ffma2_rn(TY, WX[k], IM[k]);
+    }
+}
+
+// reduce-scatter of the 8 slot sums over the env's 8 lanes (slot = v ^ part): returns |S_v|^2
+__device__ __forceinline__ float sarl_reduce_abs2(float2 (&RE)[4], float2 (&IM)[4]) {
+    float2 r0 = __fadd2_rn(RE[0], shfl_xor2(RE[2], 4)), r1 = __fadd2_rn(RE[1], shfl_xor2(RE[3], 4));
+    float2 i0 = __fadd2_rn(IM[0], shfl_xor2(IM[2], 4)), i1 = __fadd2_rn(IM[1], shfl_xor2(IM[3], 4));
+    r0 = __fadd2_rn(r0, shfl_xor2(r1, 2));
+    i0 = __fadd2_rn(i0, shfl_xor2(i1, 2));
+    const float sr = r0.x + __shfl_xor_sync(kFull, r0.y, 1);
+    const float si = i0.x + __shfl_xor_sync(kFull, i0.y, 1);
+    return sr * sr + si * si;
+}
+
+template <int MPI, bool MFULL, bool FULL>
 __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t p, SarlArgs a) {
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31, el = lane >> 3, part = lane & 7;
     const int E = d.E, V = d.V, M = d.M, T = a.T;
-    if (warp * 4 >= E) return;
-    const int e = warp * 4 + el, v = part;
-    const bool env_ok = e < E;
+    const int e_raw = blockIdx.x * 4 + el;
+    const bool env_ok = e_raw < E;
+    const int e = min(e_raw, E - 1), v = part, vc = min(v, V - 1);  // clamped copies are load-only
     const bool act = env_ok && v < V;
-    const size_t ev = (size_t)e * V + v;
+    const size_t ev = (size_t)e * V + vc;
 
-    // ---- geometry phasors of my elements for all 8 vehicles -> registers
+    // ---- geometry phasors of my elements for the 8 vehicles (slot = v ^ part) -> registers
     float2 WX[MPI][4], WY[MPI][4];
     {
-        const double my_delta = act ? d.angle_BR - s.angle[ev] : 0.0;
+        const double my_delta = d.angle_BR - s.angle[ev];
 #pragma unroll
-        for (int v2 = 0; v2 < 8; ++v2) {
+        for (int sl = 0; sl < 8; ++sl) {
+            const int v2 = sl ^ part;
             const double dv = __shfl_sync(kFull, my_delta, (lane & ~7) + v2);
             const bool ok2 = env_ok && v2 < V;
 #pragma unroll
@@ -476,140 +509,149 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
                 const int m = part + 8 * i;
                 float re = 0.f, im = 0.f;
                 if (ok2 && m < M) phasor_f32((double)m * dv, &re, &im);
-                if (v2 & 1) { WX[i][v2 >> 1].y = re; WY[i][v2 >> 1].y = im; }
-                else        { WX[i][v2 >> 1].x = re; WY[i][v2 >> 1].x = im; }
+                if (sl & 1) { WX[i][sl >> 1].y = re; WY[i][sl >> 1].y = im; }
+                else        { WX[i][sl >> 1].x = re; WY[i][sl >> 1].x = im; }
             }
         }
     }
-    double buf = act ? s.databuf[ev] : 0.0;
-    const float coef = act ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
-    const long long step0 = env_ok ? s.step_ctr[e] : 0;
+    double buf = s.databuf[ev];
+    const float coef = (float)(s.amp[ev] / (kSigma * kSigma));  // SARL:157-159
+    const long long step0 = s.step_ctr[e];
     const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
     const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);  // SARL:331
     const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));        // SARL:318-319
     const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
     const float invV = 1.0f / (float)V;
     const float lam = (float)p.rate;
-    const bool b2 = part & 4, b1 = part & 2, b0 = part & 1;
+    const double tf = p.time_fast;
 
-    auto load_in = [&](SarlStepIn<MPI>& in, int t) {
-        const float* ph_t = a.phase + ((size_t)t * E + e) * M;
+    // ---- per-lane stream pointers; every stream advances by a warp-uniform stride per step
+    const size_t sM = (size_t)E * M, s2V = (size_t)E * 2 * V, sV = (size_t)E * V;
+    const float* ph_p = a.phase + (size_t)e * M + part;
+    const float* ac_p = a.action + (size_t)e * 2 * V + vc;
+    const int* ar_p = (FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr;
+    float* o_buf = a.out.DataBuf ? a.out.DataBuf + ev : nullptr;
+    float* o_dt = a.out.data_t ? a.out.data_t + ev : nullptr;
+    float* o_dp = a.out.data_p ? a.out.data_p + ev : nullptr;
+    float* o_op = a.out.over_power ? a.out.over_power + ev : nullptr;
+    float* o_od = a.out.over_data ? a.out.over_data + ev : nullptr;
+    float* o_rt = a.out.rate ? a.out.rate + ev : nullptr;
+    float* o_rw = a.out.reward ? a.out.reward + e : nullptr;
+
+    auto load_in = [&](SarlStepIn<MPI>& in, size_t k) {  // inputs of the step k strides ahead
 #pragma unroll
-        for (int i = 0; i < MPI; ++i) {
-            const int m = part + 8 * i;
-            in.ph[i] = (env_ok && m < M) ? __ldg(ph_t + m) : 0.f;
-        }
-        const size_t ta = ((size_t)t * E + e) * 2 * V + v;
-        in.a0 = act ? __ldg(a.action + ta) : 0.f;
-        in.a1 = act ? __ldg(a.action + ta + V) : 0.f;
-        in.arr = (act && a.arrivals != nullptr) ? __ldg(a.arrivals + ((size_t)t * E + e) * V + v) : 0;
+        for (int i = 0; i < MPI; ++i)
+            in.ph[i] = (MFULL || part + 8 * i < M) ? __ldg(ph_p + k * sM + 8 * i) : 0.f;
+        in.a0 = __ldg(ac_p + k * s2V);
+        in.a1 = __ldg(ac_p + k * s2V + V);
+        in.arr = (FULL || ar_p != nullptr) ? __ldg(ar_p + k * sV) : 0;
     };
 
-    SarlStepIn<MPI> cur[U], nxt[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (u < T) load_in(cur[u], u);
+    float l_rate = 0.f, l_dt = 0.f, l_dp = 0.f, l_overp = 0.f, l_overd = 0.f, l_rew = 0.f;
+    int l_arr = 0;
 
-    float o_rate = 0.f, o_dt = 0.f, o_dp = 0.f, o_overp = 0.f, o_overd = 0.f, o_rew = 0.f;
-    int o_arr = 0;
-
-    for (int t0 = 0; t0 < T; t0 += U) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (t0 + U + u < T) load_in(nxt[u], t0 + U + u);
-
-        // ---- state-independent part of the U steps
-        float rate[U], data_t[U], data_p[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            float2 RE[4], IM[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) RE[k] = IM[k] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < MPI; ++i) {
-                float sn, cs;
-                sincos_fast(cur[u].ph[i], &sn, &cs);  // theta_m = exp(j*phase_m), SARL:125-131
-                const float2 TX = make_float2(cs, cs), TY = make_float2(sn, sn), NTY = make_float2(-sn, -sn);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {  // theta_m * w_vm for the vehicle pair (2k, 2k+1)
-                    RE[k] = __ffma2_rn(TX, WX[i][k], RE[k]);
-                    RE[k] = __ffma2_rn(NTY, WY[i][k], RE[k]);
-                    IM[k] = __ffma2_rn(TX, WY[i][k], IM[k]);
-                    IM[k] = __ffma2_rn(TY, WX[i][k], IM[k]);
-                }
-            }
-            // reduce-scatter over the env's 8 lanes: lane `part` ends with vehicle v = part
-            float2 r0 = b2 ? RE[2] : RE[0], r1 = b2 ? RE[3] : RE[1];
-            float2 i0 = b2 ? IM[2] : IM[0], i1 = b2 ? IM[3] : IM[1];
-            r0 = add2(r0, shfl_xor2(b2 ? RE[0] : RE[2], 4)); r1 = add2(r1, shfl_xor2(b2 ? RE[1] : RE[3], 4));
-            i0 = add2(i0, shfl_xor2(b2 ? IM[0] : IM[2], 4)); i1 = add2(i1, shfl_xor2(b2 ? IM[1] : IM[3], 4));
-            float2 r = add2(b1 ? r1 : r0, shfl_xor2(b1 ? r0 : r1, 2));
-            float2 im = add2(b1 ? i1 : i0, shfl_xor2(b1 ? i0 : i1, 2));
-            const float sr = (b0 ? r.y : r.x) + __shfl_xor_sync(kFull, b0 ? r.x : r.y, 1);
-            const float si = (b0 ? im.y : im.x) + __shfl_xor_sync(kFull, b0 ? im.x : im.y, 1);
-
-            const float g2 = sr * sr + si * si;
-            rate[u] = log1pf(cur[u].a0 * (coef * g2));  // natural log, SARL:159
-            data_t[u] = rate[u] * c_dt;
-            data_p[u] = cbrtf(cur[u].a1) * c_dp;
+    // sequential part of one step (SARL:333-358); k = stride offset of the step's outputs
+    auto scan_step = [&](const SarlStepIn<MPI>& in, float rate, float data_t, float data_p, int t, size_t k) {
+        int arr = in.arr;
+        if (!FULL && ar_p == nullptr) arr = act ? draw_arrival(d, e, v, step0 + t, lam) : 0;
+        double nb = buf - ((double)data_t + (double)data_p);
+        float overp = 0.f, overd = 0.f;
+        if (nb < 0.0) {
+            const float b = (float)fmax(0.0, nb + (double)data_p) * c_rev;
+            overp = in.a1 - b * b * b;
+            overd = (float)(-nb);
+            nb = 0.0;
         }
-
-        // ---- DataBuf recursion and reward, sequential over the U steps (SARL:333-358)
+        const float nbf = (float)nb;
+        const float base = -(t1 * (in.a0 + in.a1)) - (t2 * nbf);
+        const float ru = (nb > 0.0) ? base - pen1 : ((overd > 2.0f) ? base - pen2 : base);
+        const float rew = seg_sum<8>(act ? ru : 0.f) * invV;
+        buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, tf), 1000.0));
+        if (act) {
+            if (FULL || o_buf) o_buf[k * sV] = (float)buf;
+            if (FULL || o_dt) o_dt[k * sV] = data_t;
+            if (FULL || o_dp) o_dp[k * sV] = data_p;
+            if (FULL || o_op) o_op[k * sV] = overp;
+            if (FULL || o_od) o_od[k * sV] = overd;
+            if (FULL || o_rt) o_rt[k * sV] = rate;
+            if (v == 0 && (FULL || o_rw)) o_rw[k * (size_t)E] = rew;
+        }
+        if (t == T - 1) {
+            l_rate = rate; l_dt = data_t; l_dp = data_p; l_overp = overp; l_overd = overd; l_rew = rew; l_arr = arr;
+            if (env_ok) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t0 + u;
-            if (t < T) {
-                const float a0 = cur[u].a0, a1 = cur[u].a1;
-                int arr = cur[u].arr;
-                if (act && a.arrivals == nullptr) arr = draw_arrival(d, e, v, step0 + t, lam);
-                double nb = buf - ((double)data_t[u] + (double)data_p[u]);
-                float overp = 0.f, overd = 0.f;
-                if (nb < 0.0) {
-                    const float b = (float)fmax(0.0, nb + (double)data_p[u]) * c_rev;
-                    overp = a1 - b * b * b;
-                    overd = (float)(-nb);
-                    nb = 0.0;
-                }
-                const float nbf = (float)nb;
-                const float base = -(t1 * (a0 + a1)) - (t2 * nbf);
-                const float ru = (nb > 0.0) ? base - pen1 : ((overd > 2.0f) ? base - pen2 : base);
-                const float rew = seg_sum<8>(act ? ru : 0.f) * invV;
-                buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, p.time_fast), 1000.0));
-                if (act) {
-                    const size_t tev = ((size_t)t * E + e) * V + v;
-                    if (a.out.DataBuf != nullptr) a.out.DataBuf[tev] = (float)buf;
-                    if (a.out.data_t != nullptr) a.out.data_t[tev] = data_t[u];
-                    if (a.out.data_p != nullptr) a.out.data_p[tev] = data_p[u];
-                    if (a.out.over_power != nullptr) a.out.over_power[tev] = overp;
-                    if (a.out.over_data != nullptr) a.out.over_data[tev] = overd;
-                    if (a.out.rate != nullptr) a.out.rate[tev] = rate[u];
-                    if (v == 0 && a.out.reward != nullptr) a.out.reward[(size_t)t * E + e] = rew;
-                }
-                if (t == T - 1) {
-                    o_rate = rate[u]; o_dt = data_t[u]; o_dp = data_p[u]; o_overp = overp; o_overd = overd;
-                    o_rew = rew; o_arr = arr;
-#pragma unroll
-                    for (int i = 0; i < MPI; ++i) {  // elements_phase_shift_real = action_phase
-                        const int m = part + 8 * i;
-                        if (env_ok && m < M) s.phase_real[(size_t)e * M + m] = cur[u].ph[i];
-                    }
-                }
+                for (int i = 0; i < MPI; ++i)  // elements_phase_shift_real = action_phase
+                    if (MFULL || part + 8 * i < M) s.phase_real[(size_t)e * M + part + 8 * i] = in.ph[i];
             }
         }
+    };
+
+    auto advance = [&](size_t k) {
+        ph_p += k * sM; ac_p += k * s2V;
+        if (FULL || ar_p) ar_p += k * sV;
+        if (FULL || o_buf) o_buf += k * sV;
+        if (FULL || o_dt) o_dt += k * sV;
+        if (FULL || o_dp) o_dp += k * sV;
+        if (FULL || o_op) o_op += k * sV;
+        if (FULL || o_od) o_od += k * sV;
+        if (FULL || o_rt) o_rt += k * sV;
+        if (FULL || o_rw) o_rw += k * (size_t)E;
+    };
+
+    SarlStepIn<MPI> c0, c1, n0, n1;
+    load_in(c0, 0);
+    if (T > 1) load_in(c1, 1); else c1 = c0;
+
+    int t = 0;
+    for (; t + 2 <= T; t += 2) {
+        // prefetch the next two steps (clamped to the last valid step at the end of the rollout)
+        load_in(n0, (t + 2 < T) ? 2 : 1);
+        load_in(n1, (t + 3 < T) ? 3 : 1);
+
+        float2 RE0[4], IM0[4], RE1[4], IM1[4];
 #pragma unroll
-        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+        for (int k = 0; k < 4; ++k) RE0[k] = IM0[k] = RE1[k] = IM1[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < MPI; ++i) {
+            float2 sn, cs;  // .x: step t, .y: step t + 1  (theta_m = exp(j*phase_m), SARL:125-131)
+            sincos_fast2(make_float2(c0.ph[i], c1.ph[i]), &sn, &cs);
+            sarl_mac(cs.x, sn.x, WX[i], WY[i], RE0, IM0);
+            sarl_mac(cs.y, sn.y, WX[i], WY[i], RE1, IM1);
+        }
+        const float g0 = sarl_reduce_abs2(RE0, IM0), g1 = sarl_reduce_abs2(RE1, IM1);
+        const float rate0 = log1pf(c0.a0 * (coef * g0)), rate1 = log1pf(c1.a0 * (coef * g1));  // SARL:159
+        const float dp0 = cbrtf(c0.a1) * c_dp, dp1 = cbrtf(c1.a1) * c_dp;
+        scan_step(c0, rate0, rate0 * c_dt, dp0, t, 0);
+        scan_step(c1, rate1, rate1 * c_dt, dp1, t + 1, 1);
+        advance(2);
+        c0 = n0; c1 = n1;
+    }
+    if (t < T) {  // odd tail (and the plain single step T = 1): pair the elements within the step
+        float2 RE0[4], IM0[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) RE0[k] = IM0[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < MPI; i += 2) {
+            float2 sn, cs;
+            sincos_fast2(make_float2(c0.ph[i], (i + 1 < MPI) ? c0.ph[i + 1] : 0.f), &sn, &cs);
+            sarl_mac(cs.x, sn.x, WX[i], WY[i], RE0, IM0);
+            if (i + 1 < MPI) sarl_mac(cs.y, sn.y, WX[i + 1], WY[i + 1], RE0, IM0);
+        }
+        const float g0 = sarl_reduce_abs2(RE0, IM0);
+        const float rate0 = log1pf(c0.a0 * (coef * g0));
+        scan_step(c0, rate0, rate0 * c_dt, cbrtf(c0.a1) * c_dp, t, 0);
     }
 
     if (act && T > 0) {
         s.databuf[ev] = buf;
-        s.rate[ev] = o_rate;
-        s.data_t[ev] = o_dt;
-        s.data_p[ev] = o_dp;
-        s.over_power[ev] = o_overp;
-        s.over_data[ev] = o_overd;
-        s.data_r[ev] = o_arr;
+        s.rate[ev] = l_rate;
+        s.data_t[ev] = l_dt;
+        s.data_p[ev] = l_dp;
+        s.over_power[ev] = l_overp;
+        s.over_data[ev] = l_overd;
+        s.data_r[ev] = l_arr;
         if (v == 0) {
-            s.reward[e] = o_rew;
+            s.reward[e] = l_rew;
             s.step_ctr[e] = step0 + T;
         }
     }

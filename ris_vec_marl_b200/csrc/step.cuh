@@ -454,13 +454,6 @@ __device__ __forceinline__ float2 shfl_xor2(float2 x, int o) {
     return make_float2(__shfl_xor_sync(kFull, x.x, o), __shfl_xor_sync(kFull, x.y, o));
 }
 
-template <int MPI>
-struct SarlStepIn {
-    float ph[MPI];
-    float a0, a1;
-    int arr;
-};
-
 // theta_m * w[slot] accumulated for the 4 slot pairs of one element
 __device__ __forceinline__ void sarl_mac(float cs, float sn, const float2 (&WX)[4], const float2 (&WY)[4],
                                          float2 (&RE)[4], float2 (&IM)[4]) {
@@ -484,6 +477,14 @@ __device__ __forceinline__ float sarl_reduce_abs2(float2 (&RE)[4], float2 (&IM)[
     const float si = i0.x + __shfl_xor_sync(kFull, i0.y, 1);
     return sr * sr + si * si;
 }
+
+struct SarlScalarIn {  // what the sequential part of a step needs from its inputs
+    float a0, a1;
+    int arr;
+};
+struct SarlHeavyOut {  // state-independent results of a step
+    float rate, data_p;
+};
 
 template <int MPI, bool MFULL, bool FULL>
 __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t p, SarlArgs a) {
@@ -525,123 +526,133 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
     const float lam = (float)p.rate;
     const double tf = p.time_fast;
 
-    // ---- per-lane stream pointers; every stream advances by a warp-uniform stride per step
-    const size_t sM = (size_t)E * M, s2V = (size_t)E * 2 * V, sV = (size_t)E * V;
-    const float* ph_p = a.phase + (size_t)e * M + part;
-    const float* ac_p = a.action + (size_t)e * 2 * V + vc;
-    const int* ar_p = (FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr;
-    float* o_buf = a.out.DataBuf ? a.out.DataBuf + ev : nullptr;
-    float* o_dt = a.out.data_t ? a.out.data_t + ev : nullptr;
-    float* o_dp = a.out.data_p ? a.out.data_p + ev : nullptr;
-    float* o_op = a.out.over_power ? a.out.over_power + ev : nullptr;
-    float* o_od = a.out.over_data ? a.out.over_data + ev : nullptr;
-    float* o_rt = a.out.rate ? a.out.rate + ev : nullptr;
-    float* o_rw = a.out.reward ? a.out.reward + e : nullptr;
+    // ---- per-lane stream bases; step t of a stream sits t * (warp-uniform 32-bit stride) further
+    // (the host checks that every stride fits 32 bits; the product is formed in 64 bits)
+    const unsigned sM = (unsigned)E * M, s2V = (unsigned)E * 2 * V, sV = (unsigned)E * V, sE = (unsigned)E;
+    const float* const ph_b = a.phase + (size_t)e * M + part;
+    const float* const ac_b = a.action + (size_t)e * 2 * V + vc;
+    const int* const ar_b = (FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr;
+    float* const o_buf = a.out.DataBuf ? a.out.DataBuf + ev : nullptr;
+    float* const o_dt = a.out.data_t ? a.out.data_t + ev : nullptr;
+    float* const o_dp = a.out.data_p ? a.out.data_p + ev : nullptr;
+    float* const o_op = a.out.over_power ? a.out.over_power + ev : nullptr;
+    float* const o_od = a.out.over_data ? a.out.over_data + ev : nullptr;
+    float* const o_rt = a.out.rate ? a.out.rate + ev : nullptr;
+    float* const o_rw = a.out.reward ? a.out.reward + e : nullptr;
+    const unsigned Tm1 = (unsigned)(T - 1);
 
-    auto load_in = [&](SarlStepIn<MPI>& in, size_t k) {  // inputs of the step k strides ahead
+    auto load_ph = [&](float (&ph)[MPI], unsigned t) {
+        const float* q = ph_b + (size_t)min(t, Tm1) * sM;
 #pragma unroll
-        for (int i = 0; i < MPI; ++i)
-            in.ph[i] = (MFULL || part + 8 * i < M) ? __ldg(ph_p + k * sM + 8 * i) : 0.f;
-        in.a0 = __ldg(ac_p + k * s2V);
-        in.a1 = __ldg(ac_p + k * s2V + V);
-        in.arr = (FULL || ar_p != nullptr) ? __ldg(ar_p + k * sV) : 0;
+        for (int i = 0; i < MPI; ++i) ph[i] = (MFULL || part + 8 * i < M) ? __ldg(q + 8 * i) : 0.f;
+    };
+    auto load_sc = [&](SarlScalarIn& in, unsigned t) {
+        const unsigned tc = min(t, Tm1);
+        const float* q = ac_b + (size_t)tc * s2V;
+        in.a0 = __ldg(q);
+        in.a1 = __ldg(q + V);
+        in.arr = (FULL || ar_b != nullptr) ? __ldg(ar_b + (size_t)tc * sV) : 0;
     };
 
-    float l_rate = 0.f, l_dt = 0.f, l_dp = 0.f, l_overp = 0.f, l_overd = 0.f, l_rew = 0.f;
-    int l_arr = 0;
-
-    // sequential part of one step (SARL:333-358); k = stride offset of the step's outputs
-    auto scan_step = [&](const SarlStepIn<MPI>& in, float rate, float data_t, float data_p, int t, size_t k) {
-        int arr = in.arr;
-        if (!FULL && ar_p == nullptr) arr = act ? draw_arrival(d, e, v, step0 + t, lam) : 0;
-        double nb = buf - ((double)data_t + (double)data_p);
-        float overp = 0.f, overd = 0.f;
-        if (nb < 0.0) {
-            const float b = (float)fmax(0.0, nb + (double)data_p) * c_rev;
-            overp = in.a1 - b * b * b;
-            overd = (float)(-nb);
-            nb = 0.0;
-        }
-        const float nbf = (float)nb;
-        const float base = -(t1 * (in.a0 + in.a1)) - (t2 * nbf);
-        const float ru = (nb > 0.0) ? base - pen1 : ((overd > 2.0f) ? base - pen2 : base);
-        const float rew = seg_sum<8>(act ? ru : 0.f) * invV;
-        buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, tf), 1000.0));
-        if (act) {
-            if (FULL || o_buf) o_buf[k * sV] = (float)buf;
-            if (FULL || o_dt) o_dt[k * sV] = data_t;
-            if (FULL || o_dp) o_dp[k * sV] = data_p;
-            if (FULL || o_op) o_op[k * sV] = overp;
-            if (FULL || o_od) o_od[k * sV] = overd;
-            if (FULL || o_rt) o_rt[k * sV] = rate;
-            if (v == 0 && (FULL || o_rw)) o_rw[k * (size_t)E] = rew;
-        }
-        if (t == T - 1) {
-            l_rate = rate; l_dt = data_t; l_dp = data_p; l_overp = overp; l_overd = overd; l_rew = rew; l_arr = arr;
-            if (env_ok) {
-#pragma unroll
-                for (int i = 0; i < MPI; ++i)  // elements_phase_shift_real = action_phase
-                    if (MFULL || part + 8 * i < M) s.phase_real[(size_t)e * M + part + 8 * i] = in.ph[i];
-            }
-        }
+    auto prefetch_l2 = [&](unsigned t) {  // the warp's 640 B phase row + 256 B action row of step t
+        const unsigned tc = min(t, Tm1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ph_b + (size_t)tc * sM + 8 * (lane >> 3)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ac_b + (size_t)tc * s2V + ((lane & 8) ? V : 0)));
     };
 
-    auto advance = [&](size_t k) {
-        ph_p += k * sM; ac_p += k * s2V;
-        if (FULL || ar_p) ar_p += k * sV;
-        if (FULL || o_buf) o_buf += k * sV;
-        if (FULL || o_dt) o_dt += k * sV;
-        if (FULL || o_dp) o_dp += k * sV;
-        if (FULL || o_op) o_op += k * sV;
-        if (FULL || o_od) o_od += k * sV;
-        if (FULL || o_rt) o_rt += k * sV;
-        if (FULL || o_rw) o_rw += k * (size_t)E;
-    };
-
-    SarlStepIn<MPI> c0, c1, n0, n1;
-    load_in(c0, 0);
-    if (T > 1) load_in(c1, 1); else c1 = c0;
-
-    int t = 0;
-    for (; t + 2 <= T; t += 2) {
-        // prefetch the next two steps (clamped to the last valid step at the end of the rollout)
-        load_in(n0, (t + 2 < T) ? 2 : 1);
-        load_in(n1, (t + 3 < T) ? 3 : 1);
-
+    // state-independent part of two steps: theta = exp(j*phase) (packed over the two steps),
+    // cascaded reduction, rate = ln(1 + a0 * coef * |S|^2) (SARL:159), data_p (SARL:331)
+    auto heavy = [&](const float (&ph0)[MPI], const float (&ph1)[MPI], const SarlScalarIn& i0, const SarlScalarIn& i1,
+                     SarlHeavyOut& h0, SarlHeavyOut& h1) {
         float2 RE0[4], IM0[4], RE1[4], IM1[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) RE0[k] = IM0[k] = RE1[k] = IM1[k] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < MPI; ++i) {
-            float2 sn, cs;  // .x: step t, .y: step t + 1  (theta_m = exp(j*phase_m), SARL:125-131)
-            sincos_fast2(make_float2(c0.ph[i], c1.ph[i]), &sn, &cs);
+            float2 sn, cs;
+            sincos_fast2(make_float2(ph0[i], ph1[i]), &sn, &cs);
             sarl_mac(cs.x, sn.x, WX[i], WY[i], RE0, IM0);
             sarl_mac(cs.y, sn.y, WX[i], WY[i], RE1, IM1);
         }
         const float g0 = sarl_reduce_abs2(RE0, IM0), g1 = sarl_reduce_abs2(RE1, IM1);
-        const float rate0 = log1pf(c0.a0 * (coef * g0)), rate1 = log1pf(c1.a0 * (coef * g1));  // SARL:159
-        const float dp0 = cbrtf(c0.a1) * c_dp, dp1 = cbrtf(c1.a1) * c_dp;
-        scan_step(c0, rate0, rate0 * c_dt, dp0, t, 0);
-        scan_step(c1, rate1, rate1 * c_dt, dp1, t + 1, 1);
-        advance(2);
-        c0 = n0; c1 = n1;
-    }
-    if (t < T) {  // odd tail (and the plain single step T = 1): pair the elements within the step
-        float2 RE0[4], IM0[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) RE0[k] = IM0[k] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < MPI; i += 2) {
-            float2 sn, cs;
-            sincos_fast2(make_float2(c0.ph[i], (i + 1 < MPI) ? c0.ph[i + 1] : 0.f), &sn, &cs);
-            sarl_mac(cs.x, sn.x, WX[i], WY[i], RE0, IM0);
-            if (i + 1 < MPI) sarl_mac(cs.y, sn.y, WX[i + 1], WY[i + 1], RE0, IM0);
-        }
-        const float g0 = sarl_reduce_abs2(RE0, IM0);
-        const float rate0 = log1pf(c0.a0 * (coef * g0));
-        scan_step(c0, rate0, rate0 * c_dt, cbrtf(c0.a1) * c_dp, t, 0);
-    }
+        h0.rate = log1pf(i0.a0 * (coef * g0));
+        h1.rate = log1pf(i1.a0 * (coef * g1));
+        h0.data_p = cbrtf(i0.a1) * c_dp;
+        h1.data_p = cbrtf(i1.a1) * c_dp;
+    };
 
+    float l_rate = 0.f, l_dt = 0.f, l_dp = 0.f, l_overp = 0.f, l_overd = 0.f, l_rew = 0.f;
+    int l_arr = 0;
+
+    // sequential part of one step (SARL:333-358), branch-free so that it can be interleaved
+    // with the next pair's heavy part
+    auto scan_step = [&](const SarlScalarIn& in, const SarlHeavyOut& h, unsigned t) {
+        int arr = in.arr;
+        if (!FULL && ar_b == nullptr) arr = act ? draw_arrival(d, e, v, step0 + t, lam) : 0;
+        const float data_t = h.rate * c_dt;
+        const double raw = buf - ((double)data_t + (double)h.data_p);  // SARL:334
+        const bool neg = raw < 0.0;
+        const float b = (float)fmax(0.0, raw + (double)h.data_p) * c_rev;
+        const float overp = neg ? in.a1 - b * b * b : 0.f;  // SARL:337
+        const float overd = neg ? (float)(-raw) : 0.f;
+        const double nb = neg ? 0.0 : raw;
+        const float base = -(t1 * (in.a0 + in.a1)) - (t2 * (float)nb);
+        const float pen = (nb > 0.0) ? pen1 : ((overd > 2.0f) ? pen2 : 0.f);  // SARL:343-352
+        const float ru = base - pen;
+        const float rew = seg_sum<8>(act ? ru : 0.f) * invV;
+        buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, tf), 1000.0));  // SARL:354-356
+        if (act) {
+            const size_t o = (size_t)t * sV;
+            if (FULL || o_buf) o_buf[o] = (float)buf;
+            if (FULL || o_dt) o_dt[o] = data_t;
+            if (FULL || o_dp) o_dp[o] = h.data_p;
+            if (FULL || o_op) o_op[o] = overp;
+            if (FULL || o_od) o_od[o] = overd;
+            if (FULL || o_rt) o_rt[o] = h.rate;
+            if (v == 0 && (FULL || o_rw)) o_rw[(size_t)t * sE] = rew;
+        }
+        l_rate = h.rate; l_dt = data_t; l_dp = h.data_p; l_overp = overp; l_overd = overd; l_rew = rew; l_arr = arr;
+    };
+
+    // ---- software pipeline over pairs of steps: in one iteration the inputs of pair p + 2 are
+    // requested, pair p + 1 runs its heavy part and pair p is scanned.  Two input buffers (X, Y)
+    // alternate roles, so the loop is written for two pairs per trip.
+    float phX0[MPI], phX1[MPI], phY0[MPI], phY1[MPI];
+    SarlScalarIn c0, c1, x0, x1, y0, y1;
+    SarlHeavyOut h0, h1, g0, g1;
+    load_ph(phX0, 0); load_ph(phX1, 1);
+    load_sc(c0, 0); load_sc(c1, 1);
+    load_ph(phY0, 2); load_ph(phY1, 3);
+    load_sc(y0, 2); load_sc(y1, 3);
+    heavy(phX0, phX1, c0, c1, h0, h1);
+    const unsigned P = (unsigned)T >> 1;
+    // invariant at the top of a trip for pair pr: (c, h) = scalars + heavy results of pair pr,
+    // buffer Y = inputs of pair pr + 1 (requested earlier), buffer X = free
+    auto trip = [&](float (&phL0)[MPI], float (&phL1)[MPI], SarlScalarIn& l0, SarlScalarIn& l1,
+                    float (&phU0)[MPI], float (&phU1)[MPI], SarlScalarIn& u0, SarlScalarIn& u1, unsigned pr) {
+        const unsigned t = 2 * pr;
+        prefetch_l2(t + 8); prefetch_l2(t + 9);      // pair pr + 4 -> L2 (no register cost)
+        load_ph(phL0, t + 4); load_ph(phL1, t + 5);  // pair pr + 2 -> the free buffer
+        load_sc(l0, t + 4); load_sc(l1, t + 5);
+        heavy(phU0, phU1, u0, u1, g0, g1);            // pair pr + 1 (clamped past the end: unused)
+        scan_step(c0, h0, t);
+        scan_step(c1, h1, t + 1);
+        c0 = u0; c1 = u1; h0 = g0; h1 = g1;
+    };
+    unsigned pr = 0;
+    for (; pr + 2 <= P; pr += 2) {
+        trip(phX0, phX1, x0, x1, phY0, phY1, y0, y1, pr);
+        trip(phY0, phY1, y0, y1, phX0, phX1, x0, x1, pr + 1);
+    }
+    if (pr < P) trip(phX0, phX1, x0, x1, phY0, phY1, y0, y1, pr);
+    if (T & 1) scan_step(c0, h0, Tm1);
+
+    if (env_ok && T > 0) {  // elements_phase_shift_real = the last action_phase (SARL:128)
+        const float* q = ph_b + (size_t)Tm1 * sM;
+#pragma unroll
+        for (int i = 0; i < MPI; ++i)
+            if (MFULL || part + 8 * i < M) s.phase_real[(size_t)e * M + part + 8 * i] = __ldg(q + 8 * i);
+    }
     if (act && T > 0) {
         s.databuf[ev] = buf;
         s.rate[ev] = l_rate;

@@ -475,7 +475,7 @@ __device__ __forceinline__ float sarl_reduce_abs2(float2 (&RE)[4], float2 (&IM)[
     i0 = __fadd2_rn(i0, shfl_xor2(i1, 2));
     const float sr = r0.x + __shfl_xor_sync(kFull, r0.y, 1);
     const float si = i0.x + __shfl_xor_sync(kFull, i0.y, 1);
-    return sr * sr + si * si;
+    return __fmaf_rn(sr, sr, __fmul_rn(si, si));
 }
 
 struct SarlScalarIn {  // what the sequential part of a step needs from its inputs
@@ -575,10 +575,10 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
             sarl_mac(cs.y, sn.y, WX[i], WY[i], RE1, IM1);
         }
         const float g0 = sarl_reduce_abs2(RE0, IM0), g1 = sarl_reduce_abs2(RE1, IM1);
-        h0.rate = log1pf(i0.a0 * (coef * g0));
-        h1.rate = log1pf(i1.a0 * (coef * g1));
-        h0.data_p = cbrtf(i0.a1) * c_dp;
-        h1.data_p = cbrtf(i1.a1) * c_dp;
+        h0.rate = log1pf(__fmul_rn(i0.a0, __fmul_rn(coef, g0)));
+        h1.rate = log1pf(__fmul_rn(i1.a0, __fmul_rn(coef, g1)));
+        h0.data_p = __fmul_rn(cbrtf(i0.a1), c_dp);
+        h1.data_p = __fmul_rn(cbrtf(i1.a1), c_dp);
     };
 
     float l_rate = 0.f, l_dt = 0.f, l_dp = 0.f, l_overp = 0.f, l_overd = 0.f, l_rew = 0.f;
@@ -589,17 +589,19 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
     auto scan_step = [&](const SarlScalarIn& in, const SarlHeavyOut& h, unsigned t) {
         int arr = in.arr;
         if (!FULL && ar_b == nullptr) arr = act ? draw_arrival(d, e, v, step0 + t, lam) : 0;
-        const float data_t = h.rate * c_dt;
-        const double raw = buf - ((double)data_t + (double)h.data_p);  // SARL:334
+        const float data_t = __fmul_rn(h.rate, c_dt);
+        const double raw = __dsub_rn(buf, __dadd_rn((double)data_t, (double)h.data_p));  // SARL:334
         const bool neg = raw < 0.0;
-        const float b = (float)fmax(0.0, raw + (double)h.data_p) * c_rev;
-        const float overp = neg ? in.a1 - b * b * b : 0.f;  // SARL:337
+        // (explicit _rn intrinsics: no FMA contraction, so the loop copy and the tail copy of this
+        //  code -- and therefore T = 1 launches and fused rollouts -- round identically)
+        const float b = __fmul_rn((float)fmax(0.0, raw + (double)h.data_p), c_rev);
+        const float overp = neg ? __fsub_rn(in.a1, __fmul_rn(__fmul_rn(b, b), b)) : 0.f;  // SARL:337
         const float overd = neg ? (float)(-raw) : 0.f;
         const double nb = neg ? 0.0 : raw;
-        const float base = -(t1 * (in.a0 + in.a1)) - (t2 * (float)nb);
+        const float base = __fsub_rn(-__fmul_rn(t1, __fadd_rn(in.a0, in.a1)), __fmul_rn(t2, (float)nb));
         const float pen = (nb > 0.0) ? pen1 : ((overd > 2.0f) ? pen2 : 0.f);  // SARL:343-352
-        const float ru = base - pen;
-        const float rew = seg_sum<8>(act ? ru : 0.f) * invV;
+        const float ru = __fsub_rn(base, pen);
+        const float rew = __fmul_rn(seg_sum<8>(act ? ru : 0.f), invV);
         buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, tf), 1000.0));  // SARL:354-356
         if (act) {
             const size_t o = (size_t)t * sV;

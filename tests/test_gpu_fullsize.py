@@ -1,0 +1,107 @@
+"""BASELINE.json sizes (4096 envs per GPU): the CUDA path against the batched float64 oracle
+on identical seeded inputs, plus size-independent invariants of the queue dynamics."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.env_oracle import EnvOracle, InjectedDraws, OracleParams, encode_groups
+from tests.parity import RTOL, sarl_rate_atol
+
+pytestmark = pytest.mark.gpu
+
+
+def reset_draws(rng, E, V):
+    pattern = [(0, 4), (220, 230), (10, 15), (170, 180), (10, 15), (220, 230), (10, 15), (170, 180), (10, 15)] * (V // 4)
+    pattern += [(5, 9)]
+    return np.stack([rng.integers(lo, hi, E) for lo, hi in pattern], axis=1).astype(np.int32)
+
+
+def close(got, want, atol, what, mask=None):
+    got, want = np.asarray(got, float), np.asarray(want, float)
+    bad = np.abs(got - want) > atol + RTOL * np.abs(want)
+    if mask is not None:
+        bad &= ~mask
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} out of tolerance, max abs err {np.abs(got - want)[bad].max():.3g}"
+
+
+def test_sarl_4096_envs_rollout_matches_oracle():
+    from ris_vec_marl_b200 import BatchedEnviron
+
+    E, V, M, T = 4096, 8, 40, 24
+    rng = np.random.default_rng(2024)
+    ri = reset_draws(rng, E, V)
+    mob = rng.random((E, 8 * V))
+    acts = rng.random((T, E, 2, V)).astype(np.float32)
+    phs = (rng.random((T, E, M)) * 2 * np.pi).astype(np.float32)
+    arr = rng.poisson(3.0, (T, E, V)).astype(np.int32)
+
+    env = BatchedEnviron("sarl", E, V, M)
+    env.make_new_game(ri)
+    used = env.renew_positions(mob)
+    env.compute_parms()
+    got = {k: v.cpu().numpy() for k, v in env.rollout_sarl(acts, phs, arr).items()}
+
+    d = InjectedDraws(reset_ints=ri, arrivals=arr)
+    o = EnvOracle("sarl", V, M, 3, E=E, draws=d)
+    o.make_new_game()
+    d.set_mobility_uniforms(mob)
+    o.renew_positions(); o.compute_parms()
+    assert np.array_equal(used.cpu().numpy(), d.mob_draws_used)
+    assert np.array_equal(env.pos_x.cpu().numpy(), o.pos[..., 0]) and np.array_equal(env.pos_y.cpu().numpy(), o.pos[..., 1])
+    ra = sarl_rate_atol(M)
+    for t in range(T):
+        rew, over_p = o.step_sarl(acts[t], phs[t])
+        pre = o.DataBuf - o.data_r
+        band = (np.abs(pre) < 4 * ra) | (np.abs(o.over_data - 2.0) < 4 * ra)  # reward penalties jump here
+        close(got["rate"][t], o.vehicle_rate, ra, f"rate t={t}")
+        close(got["data_p"][t], o.data_p, 1e-5, f"data_p t={t}")
+        close(got["DataBuf"][t], o.DataBuf, 4 * ra, f"DataBuf t={t}")
+        close(got["over_data"][t], o.over_data, 4 * ra, f"over_data t={t}")
+        close(got["over_power"][t], over_p, 4e-6, f"over_power t={t}")
+        close(got["reward"][t], rew, 4e-6, f"reward t={t}", mask=band.any(axis=1))
+    # invariants at full size
+    assert (got["DataBuf"] >= 0).all() and (got["over_data"] >= 0).all() and (got["rate"] >= 0).all()
+    assert np.all((got["over_data"] > 0) <= (got["DataBuf"] - arr <= 1e-6))  # overflow only when the buffer drained
+
+
+def test_marl_4096_envs_rollout_matches_oracle():
+    from ris_vec_marl_b200 import BatchedEnviron, marl_yaml_overrides
+
+    E, V, M, T = 4096, 8, 40, 12
+    rng = np.random.default_rng(77)
+    ri = reset_draws(rng, E, V)
+    mob = rng.random((E, 8 * V))
+    acts = rng.random((T, E, 2, V)).astype(np.float32)
+    acts[:, :, 1, :] = np.maximum(acts[:, :, 1, :], np.float32(0.1))
+    arr = rng.poisson(1.0, (T, E, V)).astype(np.int32)
+    part, ng = encode_groups([[0, 1], [3, 2], [4, 5], [6], [7]], V)
+    partner, ngroups = np.tile(part, (E, 1)), np.full(E, ng, dtype=np.int32)
+
+    env = BatchedEnviron("marl", E, V, M, **marl_yaml_overrides())
+    env.make_new_game(ri); env.renew_positions(mob); env.compute_parms()
+    phase0 = np.zeros((E, M), dtype=np.float32)
+    env.get_next_phase(phase0)  # theta = 1: includes destructive-interference gains
+    env.update_channel_gains()
+    got = {k: v.cpu().numpy() for k, v in env.rollout_marl(acts, partner, ngroups, arr).items()}
+
+    d = InjectedDraws(reset_ints=ri, arrivals=arr)
+    o = EnvOracle("marl", V, M, 3, E=E, params=OracleParams.marl_yaml(), draws=d)
+    o.make_new_game()
+    d.set_mobility_uniforms(mob)
+    o.renew_positions(); o.compute_parms(); o.get_next_phase(phase0.astype(np.float64)); o.update_channel_gains()
+    np.testing.assert_allclose(env.gains.cpu().numpy(), o.channel_gains, rtol=1e-7, atol=1e-26)
+    p = o.p
+    for t in range(T):
+        r_user, r_glob, over_p = o.step_marl(acts[t], partner, ngroups)
+        L = o.last
+        band = (np.abs(o.vehicle_rate - p.R_min_bpsHz) < 1e-5 * p.R_min_bpsHz) | (np.abs(L["delay"] - p.D_max_s) < 1e-5 * p.D_max_s)
+        amp = (L["edge_in_sum"] < 1e-3) & (L["q_before"] > 0) & (L["edge_in_sum"] > 0)
+        band |= amp[:, None]
+        close(got["rate"][t], o.vehicle_rate, 1e-6, f"rate t={t}")
+        close(got["data_t"][t], o.data_t, 1e-5, f"data_t t={t}")
+        close(got["data_p"][t], o.data_p, 1e-5, f"data_p t={t}")
+        close(got["DataBuf"][t], o.DataBuf, 1e-5, f"DataBuf t={t}")
+        close(got["reward_user"][t], r_user, 2e-6, f"reward_user t={t}", mask=band)
+        close(got["reward"][t], r_glob, 2e-6, f"reward t={t}", mask=band.any(axis=1))
+    np.testing.assert_allclose(env.mec_queue_cycles.cpu().numpy(), o.mec_queue_cycles, rtol=1e-6, atol=1.0)
+    assert (got["DataBuf"] >= 0).all() and (got["rate"] >= 0).all() and (np.abs(got["reward_user"]) <= 50).all()

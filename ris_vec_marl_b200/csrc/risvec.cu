@@ -423,6 +423,18 @@ int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int
     a.T = T; a.action = action; a.partner = partner; a.ngroups = ngroups; a.arrivals = arrivals;
     if (out) a.out = *out;
     cudaStream_t st = (cudaStream_t)stream;
+    if (env->dims.V <= 8 && !env->force_generic && !a.out.stats && !a.out.last_power) {
+        // fast path: 4 envs per warp, lane = vehicle (FULL = the six bench traces + injected arrivals)
+        const risvec_marl_out_t& o = a.out;
+        const bool full = arrivals && o.reward_user && o.reward && o.DataBuf && o.data_t && o.data_p && o.rate &&
+                          !o.over_power;
+        const int warps = (env->dims.E + 3) / 4;
+        if (full)
+            k_marl_v8<true><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+        else
+            k_marl_v8<false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+        return check_launch(env, "k_marl_v8");
+    }
     switch (pow2ceil(env->dims.V)) {
         case 1: return launch_marl<1>(env, a, st);
         case 2: return launch_marl<2>(env, a, st);

@@ -8,6 +8,8 @@
 // lives in registers for the whole rollout; per step only actions / phases / arrivals stream
 // in from HBM and the requested traces stream out.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace risvec {
@@ -665,6 +667,232 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
         s.data_r[ev] = l_arr;
         if (v == 0) {
             s.reward[e] = l_rew;
+            s.step_ctr[e] = step0 + T;
+        }
+    }
+}
+
+// =========================================================================================
+// MARL fast path for V <= 8 (BASELINE config 3: V = 8): one warp = 4 envs, lane = (env, vehicle)
+// =========================================================================================
+// Same pipeline shape as k_sarl_v8: two steps per trip, inputs of the next pair prefetched into
+// registers, the state-independent part of a step (power projection, NOMA/OMA rate, data_t,
+// CPU share -> f_local, cap) separated from the sequential float64 queue recursion
+// (DataBuf, MEC queue).  The `last_*` statistics are produced only for the final step of the
+// launch (they are state, not a per-step trace, in this kernel); launches that ask for the
+// `stats` / `last_power` traces use the shape-generic k_marl_rollout.
+struct MarlIn {
+    float a0, a1;
+    int arr;
+};
+struct MarlHeavy {
+    float P0, P1, rate, data_t, f_local_f;
+    double f_local, cap;
+};
+
+template <bool FULL>
+__global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t p, MarlArgs a) {
+    const int lane = threadIdx.x & 31, el = lane >> 3, v = lane & 7;
+    const int E = d.E, V = d.V, T = a.T;
+    const int e_raw = blockIdx.x * 4 + el;
+    const bool env_ok = e_raw < E;
+    const int e = min(e_raw, E - 1), vc = min(v, V - 1);
+    const bool act = env_ok && v < V;
+    const size_t ev = (size_t)e * V + vc;
+
+    double buf = act ? s.databuf[ev] : 0.0;
+    const double g = act ? s.gains[ev] : 0.0;
+    const int code = act ? a.partner[ev] : RISVEC_PARTNER_NONE;
+    const int ng = a.ngroups[e];
+    double Q = s.mecq[e];
+    const long long step0 = s.step_ctr[e];
+
+    const bool paired = code >= 0;
+    const bool second = paired && (code & RISVEC_PARTNER_SECOND);
+    int other = paired ? (code & (RISVEC_PARTNER_SECOND - 1)) : v;
+    other = min(max(other, 0), 7);
+    const int src = (lane & ~7) + other;
+    const double g_o = __shfl_sync(kFull, g, src);
+    const bool first_near = second ? (g_o > g) : (g > g_o);  // MARL:355
+    const bool near = paired ? (second ? !first_near : first_near) : true;
+    const float gn = (float)(g / p.noise_power);
+    // rate = (1/G) * log2(1 + sinr) = (log2(e)/G) * log1p(sinr); 0 when unscheduled (MARL:341-349).
+    // log1p, not log2(1 + x): with destructive-interference gains the SINR falls below 2^-24 and
+    // the reference still derives a non-zero rate (and a full-slot t_tx) from it.
+    const float frac = (code != RISVEC_PARTNER_NONE)
+                           ? (float)(1.0 / (double)max(1, ng)) * 1.44269504088896341f : 0.f;
+
+    const float ps = (float)p.power_scale, Pmax = (float)p.P_max;
+    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
+    const float c_thr = (float)(p.bandwidth * 1000.0);
+    double floor_d = p.cpu_share_floor;
+    if (!isfinite(floor_d)) floor_d = 0.10;
+    floor_d = fmax(0.0, fmin(floor_d, 0.95));
+    const float floor_f = (float)floor_d;
+    const double Cpb = p.cycles_per_bit, den = Cpb * 1000.0, tf = p.time_fast, flm = p.f_local_max;
+    const double edge_cap = p.f_edge_max * p.time_fast;
+    const float inv_fedge = (float)(1.0 / (p.f_edge_max + 1e-12));
+    const float kf = (float)p.k;
+    const float wd = (float)p.w_d, we = (float)p.w_e, pen = p.qos_enable ? (float)p.qos_penalty : 0.f;
+    const float clipv = (float)p.reward_clip;
+    const float Rmin = p.qos_enable ? (float)p.R_min_bpsHz : -1.f, Dmax = p.qos_enable ? (float)p.D_max_s : 3.0e38f;
+    const float invV = 1.0f / (float)V;
+    const float lam = (float)p.rate;
+
+    const unsigned s2V = (unsigned)E * 2 * V, sV = (unsigned)E * V, sE = (unsigned)E;
+    const float* const ac_b = a.action + (size_t)e * 2 * V + vc;
+    const int* const ar_b = (FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr;
+    float* const o_ru = a.out.reward_user ? a.out.reward_user + ev : nullptr;
+    float* const o_buf = a.out.DataBuf ? a.out.DataBuf + ev : nullptr;
+    float* const o_dt = a.out.data_t ? a.out.data_t + ev : nullptr;
+    float* const o_dp = a.out.data_p ? a.out.data_p + ev : nullptr;
+    float* const o_rt = a.out.rate ? a.out.rate + ev : nullptr;
+    float* const o_op = a.out.over_power ? a.out.over_power + ev : nullptr;
+    float* const o_rw = a.out.reward ? a.out.reward + e : nullptr;
+    const unsigned Tm1 = (unsigned)(T - 1);
+
+    auto load_in = [&](MarlIn& in, unsigned t) {
+        const unsigned tc = min(t, Tm1);
+        const float* q = ac_b + (size_t)tc * s2V;
+        in.a0 = act ? __ldg(q) : 0.f;
+        in.a1 = act ? __ldg(q + V) : 0.f;
+        in.arr = (act && (FULL || ar_b != nullptr)) ? __ldg(ar_b + (size_t)tc * sV) : 0;
+    };
+
+    // state-independent part of a step
+    auto heavy = [&](const MarlIn& in, MarlHeavy& h) {
+        float p0 = __fmul_rn(fmaxf(in.a0, 0.f), ps), p1 = __fmul_rn(fmaxf(in.a1, 0.f), ps);  // MARL:555-561
+        const float sm = __fadd_rn(p0, p1);
+        const float sc = (sm > 1.0f) ? __frcp_rn(__fadd_rn(sm, 1e-12f)) : 1.0f;
+        p0 = __fmul_rn(p0, sc); p1 = __fmul_rn(p1, sc);
+        h.P0 = __fmul_rn(p0, Pmax); h.P1 = __fmul_rn(p1, Pmax);
+        const float P0_o = __shfl_sync(kFull, h.P0, src);
+        const float sig = __fmul_rn(h.P0, gn);
+        const float sinr = near ? sig : __fdividef(sig, __fmaf_rn(P0_o, gn, 1.0f));  // MARL:362-369
+        h.rate = __fmul_rn(frac, log1pf(sinr));
+        h.data_t = __fmul_rn(h.rate, c_dt);                                             // MARL:570
+        const float share = fmaxf(fminf(fmaxf(in.a1, 0.f), 1.f), floor_f);             // MARL:572-578
+        h.f_local = __dmul_rn((double)share, flm);
+        h.cap = __dmul_rn(h.f_local, tf);
+        h.f_local_f = (float)h.f_local;
+    };
+
+    float l_rate = 0.f, l_dt = 0.f, l_dp = 0.f, l_rew = 0.f, l_glob = 0.f, l_overp = 0.f;
+    int l_arr = 0;
+
+    // sequential part of a step: local CPU, offload, MEC queue, delays, energy, reward
+    auto scan_step = [&](const MarlIn& in, const MarlHeavy& h, unsigned t, auto with_stats) {
+        int arr = in.arr;
+        if (!FULL && ar_b == nullptr) arr = act ? draw_arrival(d, e, v, step0 + t, lam) : 0;
+        const double backlog_kbit = buf;
+        const double backlog_cyc = __dmul_rn(__dmul_rn(backlog_kbit, 1000.0), Cpb);  // MARL:585-592
+        const double used = fmin(h.cap, backlog_cyc);
+        const double local_done = __ddiv_rn(used, den);
+        const double remaining = fmax(0.0, __dsub_rn(backlog_kbit, local_done));
+        const double off = fmin((double)h.data_t, remaining);                       // MARL:595-596
+        const double edge_in = __dmul_rn(__dmul_rn(off, 1000.0), Cpb);               // MARL:604
+        const double edge_sum = seg_sum<8>(edge_in);
+        const double q_before = Q;
+        Q = __dadd_rn(Q, edge_sum);
+        const double served = fmin(edge_cap, Q);
+        Q = __dsub_rn(Q, served);                                                    // MARL:606-610
+        buf = fmax(0.0, __dsub_rn(buf, __dadd_rn(local_done, off)));                 // MARL:617-618
+        buf = __dadd_rn(buf, __dmul_rn(__dmul_rn((double)arr, tf), 1000.0));         // MARL:717-719
+
+        const float off_f = (float)off, edge_in_f = (float)edge_in;
+        const float t_tx = __fdividef(off_f, __fmaf_rn(h.rate, c_thr, 1e-12f));      // MARL:599-601
+        const float d_local = __fdividef((float)fmax(0.0, __dsub_rn(backlog_cyc, edge_in)),
+                                         __fadd_rn(h.f_local_f, 1e-12f));             // MARL:623-626
+        const float sh = __fdividef(edge_in_f, (float)(edge_sum + 1e-12));           // MARL:629
+        const float d_eq = __fmul_rn(sh, __fmul_rn((float)q_before, inv_fedge));
+        const float d_ec = __fmul_rn(edge_in_f, inv_fedge);
+        const float delay = __fadd_rn(__fadd_rn(__fadd_rn(d_local, t_tx), d_eq), d_ec);  // MARL:633
+        const float E_tx = __fmul_rn(h.P0, t_tx);                                      // MARL:659-661
+        const float E_loc = __fmul_rn(__fmul_rn(__fmul_rn(kf, h.f_local_f), h.f_local_f), (float)used);
+        const float energy = __fadd_rn(E_tx, E_loc);
+        const bool viol = (h.rate < Rmin) || (delay > Dmax);                           // MARL:669-677
+        float rew = __fsub_rn(-__fmaf_rn(wd, delay, __fmul_rn(we, energy)), viol ? pen : 0.f);
+        rew = fminf(fmaxf(rew, -clipv), clipv);                                        // MARL:696-703
+        const float glob = __fmul_rn(seg_sum<8>(act ? rew : 0.f), invV);               // MARL:721
+        const float overp = fmaxf(0.f, __fsub_rn(__fadd_rn(h.P0, h.P1), Pmax));        // MARL:727-729
+        if (act) {
+            const size_t o = (size_t)t * sV;
+            if (FULL || o_ru) o_ru[o] = rew;
+            if (FULL || o_buf) o_buf[o] = (float)buf;
+            if (FULL || o_dt) o_dt[o] = h.data_t;
+            if (FULL || o_dp) o_dp[o] = (float)local_done;
+            if (FULL || o_rt) o_rt[o] = h.rate;
+            if (!FULL && o_op) o_op[o] = overp;
+            if (v == 0 && (FULL || o_rw)) o_rw[(size_t)t * sE] = glob;
+        }
+        l_rate = h.rate; l_dt = h.data_t; l_dp = (float)local_done; l_rew = rew; l_glob = glob; l_overp = overp;
+        l_arr = arr;
+        if constexpr (decltype(with_stats)::value) {  // last_* scalars (MARL:612-614,636-656,677,706-711)
+            const float m_delay = seg_sum<8>(act ? delay : 0.f) * invV;
+            const float m_energy = seg_sum<8>(act ? energy : 0.f) * invV;
+            const float m_dl = seg_sum<8>(act ? d_local : 0.f) * invV;
+            const float m_dq = seg_sum<8>(act ? d_eq : 0.f) * invV;
+            const float m_dc = seg_sum<8>(act ? d_ec : 0.f) * invV;
+            const float m_ttx = seg_sum<8>(act ? t_tx : 0.f) * invV;
+            const float m_back = seg_sum<8>(act ? (float)backlog_kbit : 0.f) * invV;
+            const float m_util = seg_sum<8>(act ? (float)(used / (h.cap + 1e-12)) : 0.f) * invV;
+            const float m_viol = seg_sum<8>((act && viol && p.qos_enable) ? 1.f : 0.f) * invV;
+            const float s_off = seg_sum<8>(act ? off_f : 0.f);
+            const float s_loc = seg_sum<8>(act ? (float)local_done : 0.f);
+            const float vals[RISVEC_NSTAT] = {m_delay, m_energy, m_dl, m_dq, m_dc, m_ttx, m_back,
+                                              (float)(served / (edge_cap + 1e-12)), m_util, m_viol, s_off, s_loc,
+                                              (float)Q, 0.f, 0.f, 0.f};
+            if (env_ok) {
+#pragma unroll
+                for (int c = 0; c < RISVEC_NSTAT; ++c)
+                    if ((c & 7) == v) s.stats[(size_t)e * RISVEC_NSTAT + c] = vals[c];
+            }
+            if (act) {
+                const float inv_tf = (float)(1.0 / p.time_fast);
+                s.last_power[(size_t)e * 2 * V + v] = E_tx * inv_tf;  // MARL:664-666
+                s.last_power[(size_t)e * 2 * V + V + v] = E_loc * inv_tf;
+            }
+        }
+    };
+
+    // all steps but the last run in pairs without statistics; the final step also produces the
+    // `last_*` state the reference exposes after a step
+    using No = std::false_type;
+    using Yes = std::true_type;
+    MarlIn c0, c1, n0, n1;
+    MarlHeavy h0, h1;
+    load_in(c0, 0); load_in(c1, 1);
+    const unsigned P = (T > 0) ? (unsigned)(T - 1) >> 1 : 0;
+    unsigned t = 0;
+    for (unsigned pr = 0; pr < P; ++pr, t += 2) {
+        load_in(n0, t + 2); load_in(n1, t + 3);
+        heavy(c0, h0); heavy(c1, h1);
+        scan_step(c0, h0, t, No{});
+        scan_step(c1, h1, t + 1, No{});
+        c0 = n0; c1 = n1;
+    }
+    if (T > 0) {
+        heavy(c0, h0);
+        if (t + 1 < (unsigned)T) {  // two steps left
+            heavy(c1, h1);
+            scan_step(c0, h0, t, No{});
+            scan_step(c1, h1, t + 1, Yes{});
+        } else {
+            scan_step(c0, h0, t, Yes{});
+        }
+    }
+
+    if (act && T > 0) {
+        s.databuf[ev] = buf;
+        s.rate[ev] = l_rate;
+        s.data_t[ev] = l_dt;
+        s.data_p[ev] = l_dp;
+        s.reward_user[ev] = l_rew;
+        s.over_power[ev] = l_overp;
+        s.data_r[ev] = l_arr;
+        if (v == 0) {
+            s.mecq[e] = Q;
+            s.reward[e] = l_glob;
             s.step_ctr[e] = step0 + T;
         }
     }

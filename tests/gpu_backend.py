@@ -10,11 +10,28 @@ def np64(t):
     return t.detach().to("cpu").numpy().astype(np.float64)
 
 
+FAST_MARL_TRACES = ("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate")
+
+
 class GpuBackend:
-    def __init__(self, g, device=0):
+    """mode="fast": the shape-specialised kernels where they apply (k_sarl_v8 / k_marl_v8; the MARL
+    one takes `last_*`, `last_power_W`, `over_power` from the state views, as the compat layer
+    does).  mode="generic": RISVEC_FORCE_GENERIC=1, the shape-generic kernels with every trace."""
+
+    def __init__(self, g, device=0, mode="fast"):
+        import os
+
         over = marl_yaml_overrides() if (g["variant"] == "marl" and g["params"] == "yaml") else {}
-        self.g = g
-        self.env = BatchedEnviron(g["variant"], g["E"], g["V"], g["M"], 3, device=device, **over)
+        self.g, self.mode = g, mode
+        old = os.environ.get("RISVEC_FORCE_GENERIC")
+        os.environ["RISVEC_FORCE_GENERIC"] = "1" if mode == "generic" else "0"
+        try:
+            self.env = BatchedEnviron(g["variant"], g["E"], g["V"], g["M"], 3, device=device, **over)
+        finally:
+            if old is None:
+                os.environ.pop("RISVEC_FORCE_GENERIC", None)
+            else:
+                os.environ["RISVEC_FORCE_GENERIC"] = old
 
     def make_new_game(self):
         g = self.g
@@ -53,17 +70,25 @@ class GpuBackend:
         return np64(self.env.mec_queue_cycles)
 
     def step_marl(self, actions, partner, ngroups, arrivals):
-        r = self.env.step_marl(actions, partner.astype(np.int32), np.asarray(ngroups, dtype=np.int32),
-                               arrivals.astype(np.int32),
-                               traces=("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate", "over_power",
-                                       "stats", "last_power"))
-        out = {k: np64(r[k]) for k in ("reward_user", "reward", "DataBuf", "data_t", "data_p", "over_power", "rate")}
-        out["last_power_W"] = np64(r["last_power"])
-        st = np64(r["stats"])
+        e = self.env
+        part, ng, arr = partner.astype(np.int32), np.asarray(ngroups, dtype=np.int32), arrivals.astype(np.int32)
+        if self.mode == "fast" and e.V <= 8:
+            r = e.step_marl(actions, part, ng, arr, traces=FAST_MARL_TRACES)
+            out = {k: np64(r[k]) for k in FAST_MARL_TRACES}
+            out["over_power"] = np64(e.over_power)
+            out["last_power_W"] = np64(e.last_power_W)
+            st = np64(e.stats)
+            assert torch.equal(e.reward_user, r["reward_user"]) and torch.equal(e.reward, r["reward"])
+        else:
+            r = e.step_marl(actions, part, ng, arr, traces=FAST_MARL_TRACES + ("over_power", "stats", "last_power"))
+            out = {k: np64(r[k]) for k in FAST_MARL_TRACES + ("over_power",)}
+            out["last_power_W"] = np64(r["last_power"])
+            st = np64(r["stats"])
+            assert torch.equal(e.stats, r["stats"])
         for i, n in enumerate(STAT_COLUMNS):
             out["last_" + n] = st[:, i]
         # the state views must agree with the traces of the same step
-        assert torch.equal(self.env.vehicle_rate, r["rate"]) and torch.equal(self.env.stats, r["stats"])
+        assert torch.equal(e.vehicle_rate, r["rate"]) and torch.equal(e.data_t, r["data_t"])
         return out
 
     def step_sarl(self, actions, phases, arrivals):

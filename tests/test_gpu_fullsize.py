@@ -82,7 +82,8 @@ def test_marl_4096_envs_rollout_matches_oracle():
     phase0 = np.zeros((E, M), dtype=np.float32)
     env.get_next_phase(phase0)  # theta = 1: includes destructive-interference gains
     env.update_channel_gains()
-    got = {k: v.cpu().numpy() for k, v in env.rollout_marl(acts, partner, ngroups, arr).items()}
+    got = {k: v.cpu().numpy() for k, v in env.rollout_marl(
+        acts, partner, ngroups, arr, traces=("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate")).items()}
 
     d = InjectedDraws(reset_ints=ri, arrivals=arr)
     o = EnvOracle("marl", V, M, 3, E=E, params=OracleParams.marl_yaml(), draws=d)

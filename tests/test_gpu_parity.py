@@ -18,25 +18,29 @@ def _need_gpu():
     load_library()  # fails loudly when the extension is missing
 
 
+@pytest.mark.parametrize("mode", ["fast", "generic"])
 @pytest.mark.parametrize("name", golden_names())
-def test_fixture_parity_single_steps(name):
+def test_fixture_parity_single_steps(name, mode):
     from tests.gpu_backend import GpuBackend
 
     g = load_golden(name)
-    got = replay(g, GpuBackend(g))
+    got = replay(g, GpuBackend(g, mode=mode))
     want = replay(g, OracleBackend(g))
     rep = compare_replays(g, got, want)
     assert rep["checked"] >= 12
 
 
-@pytest.mark.parametrize("name", ["marl_v8_m40_yaml", "sarl_v8_m40", "sarl_v32_m256", "marl_v6_m7_ragged"])
-def test_fused_rollout_equals_single_steps(name):
-    """One launch over T steps must give bit-identical traces and final state to T launches."""
-    from tests.gpu_backend import GpuBackend
+@pytest.mark.parametrize("mode", ["fast", "generic"])
+@pytest.mark.parametrize("name", ["marl_v8_m40_yaml", "sarl_v8_m40", "sarl_v32_m256", "marl_v6_m7_ragged",
+                                  "sarl_v5_m33_ragged"])
+def test_fused_rollout_equals_single_steps(name, mode):
+    """One launch over T steps must give bit-identical traces and final state to T launches
+    (odd and even T, so both the paired loop and the tail of the fast kernels are hit)."""
+    from tests.gpu_backend import FAST_MARL_TRACES, GpuBackend
 
     g = load_golden(name)
-    T = g["T"]
-    a, b = GpuBackend(g), GpuBackend(g)
+    T = g["T"] - (1 if name == "marl_v8_m40_yaml" else 0)
+    a, b = GpuBackend(g, mode=mode), GpuBackend(g, mode=mode)
     for be in (a, b):
         be.make_new_game()
         be.renew_positions(g["ep_mob_uniforms"][0])
@@ -49,16 +53,46 @@ def test_fused_rollout_equals_single_steps(name):
     if g["variant"] == "marl":
         part = g["ep_partner"][0].astype(np.int32)
         ng = np.asarray(g["ep_ngroups"][0], dtype=np.int32)
-        fused = a.env.rollout_marl(acts, part, ng, arr)
-        single = [b.env.step_marl(acts[t], part, ng, arr[t], traces=tuple(fused)) for t in range(T)]
+        tr = FAST_MARL_TRACES if mode == "fast" else FAST_MARL_TRACES + ("over_power", "stats", "last_power")
+        fused = a.env.rollout_marl(acts, part, ng, arr, traces=tr)
+        single = [b.env.step_marl(acts[t], part, ng, arr[t], traces=tr) for t in range(T)]
     else:
         ph = torch.as_tensor(g["phases"][:T]).cuda()
         fused = a.env.rollout_sarl(acts, ph, arr)
         single = [b.env.step_sarl(acts[t], ph[t], arr[t], traces=tuple(fused)) for t in range(T)]
     for k, v in fused.items():
         assert torch.equal(v, torch.stack([s[k] for s in single])), k
-    for f in ("DataBuf", "data_t", "data_p", "vehicle_rate", "reward", "mec_queue_cycles", "step_ctr", "stats"):
+    for f in ("DataBuf", "data_t", "data_p", "vehicle_rate", "reward", "reward_user", "mec_queue_cycles", "step_ctr",
+              "stats", "last_power_W", "over_power", "over_data", "data_r", "phase_real"):
         assert torch.equal(a.env.state(f), b.env.state(f)), f
+
+
+def test_fast_and_generic_kernels_agree():
+    """The shape-specialised kernels against the shape-generic ones on the same inputs:
+    identical integer/float64 state, float32 traces within a few ulp (different summation
+    trees in the cascaded reduction, MUFU log2 vs log1pf in the MARL rate)."""
+    from tests.gpu_backend import FAST_MARL_TRACES, GpuBackend
+
+    for name in ("marl_v8_m40_yaml", "sarl_v8_m40"):
+        g = load_golden(name)
+        T = g["T"]
+        envs = [GpuBackend(g, mode=m) for m in ("fast", "generic")]
+        outs = []
+        for be in envs:
+            be.make_new_game(); be.renew_positions(g["ep_mob_uniforms"][0]); be.compute_parms()
+            acts = torch.as_tensor(g["actions"][:T]).cuda()
+            arr = torch.as_tensor(g["arrivals"][:T].astype(np.int32)).cuda()
+            if g["variant"] == "marl":
+                be.optimize_phase_shift(); be.update_channel_gains()
+                outs.append(be.env.rollout_marl(acts, g["ep_partner"][0].astype(np.int32),
+                                                np.asarray(g["ep_ngroups"][0], dtype=np.int32), arr,
+                                                traces=FAST_MARL_TRACES))
+            else:
+                outs.append(be.env.rollout_sarl(acts, torch.as_tensor(g["phases"][:T]).cuda(), arr))
+        for k in outs[0]:
+            np.testing.assert_allclose(outs[0][k].cpu().numpy(), outs[1][k].cpu().numpy(), rtol=2e-5, atol=2e-5,
+                                       err_msg=f"{name}:{k}")
+        assert torch.equal(envs[0].env.data_r, envs[1].env.data_r)
 
 
 def test_host_buffer_entry_point_matches_device_path():

@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -199,8 +199,8 @@ def workload_config(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sarl", choices=["sarl", "marl"])
     ap.add_argument("--envs", type=int, default=4096, help="env instances per GPU")
@@ -271,20 +271,38 @@ def main():
         else:
             env.rollout_sarl(actions, phases, arrivals, out=out)
 
-    from ris_vec_marl_b200.dist import all_reduce_sum
+
+    pending = []
 
     def episode_stats():
-        # the only collective on the path: NCCL sum of a 17-entry f64 vector
-        stats_sum.add_(all_reduce_sum(env.shard_stats()))
+        # the only collective on the path: NCCL sum of a 17-entry f64 vector.  It is
+        # issued asynchronously (NCCL's own stream) so the next rollout overlaps it; `drain_stats`
+        # waits for all of them inside the timed region.
+        sv = env.shard_stats()
+        if world > 1:
+            pending.append((dist.all_reduce(sv, async_op=True), sv))
+        else:
+            stats_sum.add_(sv)
+
+    def drain_stats():
+        for work, sv in pending:
+            work.wait()
+            stats_sum.add_(sv)
+        pending.clear()
 
     for _ in range(args.warmup):
         one_step(); episode_stats()
+    drain_stats()
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, device-timed, max over ranks
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        for _ in range(args.warmup):  # keep the GPU under load while nvidia-smi spins up
+            one_step()
+        torch.cuda.synchronize()
+        sampler.lines.clear()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -297,6 +315,7 @@ def main():
         one_step()
         kev[i][1].record()
         episode_stats()
+    drain_stats()
     ev[1].record()
     torch.cuda.synchronize()
     if world > 1:

@@ -56,9 +56,12 @@ struct risvec_env {
     FieldDesc fields[RISVEC_F_COUNT];
     unsigned long long reset_calls, mob_calls, chan_calls;
     int64_t launches;
-    // device staging for the *_host entry points (grow-only)
+    // device staging for the *_host entry points (grow-only) + their copy pipeline
     char* stage;
     size_t stage_bytes;
+    int pipe_ready;
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev[2 * 16 + 2];
     int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
 };
 
@@ -172,19 +175,28 @@ struct Carver {
 };
 
 __global__ void k_shard_stats(Dims d, State s, double* out) {
-    // block c sums column c of the stats over the shard's envs (column NSTAT = global reward)
-    __shared__ double red[32];
-    const int c = blockIdx.x;
-    double acc = 0.0;
-    for (int e = threadIdx.x; e < d.E; e += blockDim.x)
-        acc += (c < RISVEC_NSTAT) ? (double)s.stats[(size_t)e * RISVEC_NSTAT + c] : (double)s.reward[e];
-    acc = seg_sum<32>(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    // each block sums a contiguous slab of envs for all columns (coalesced 64 B rows), then adds
+    // its 17 partial sums to `out` (zeroed by the caller) with float64 atomics
+    __shared__ double red[8][RISVEC_NSTAT + 1];
+    const int col = threadIdx.x & 15, row = threadIdx.x >> 4;  // 16 columns x 16 env rows per pass
+    const int per_block = (d.E + gridDim.x - 1) / gridDim.x;
+    const int e0 = blockIdx.x * per_block, e1 = min(d.E, e0 + per_block);
+    double acc = 0.0, racc = 0.0;
+    for (int e = e0 + row; e < e1; e += 16) {
+        acc += (double)s.stats[(size_t)e * RISVEC_NSTAT + col];
+        if (col == 0) racc += (double)s.reward[e];
+    }
+    // reduce over the 16 rows: lanes l and l ^ 16 hold the same column in one warp
+    acc += __shfl_xor_sync(kFull, acc, 16);
+    racc += __shfl_xor_sync(kFull, racc, 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 16) red[warp][lane] = acc;
+    if (lane == 0) red[warp][RISVEC_NSTAT] = racc;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-        v = seg_sum<32>(v);
-        if (threadIdx.x == 0) out[c] = v;
+    if (threadIdx.x <= RISVEC_NSTAT) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        atomicAdd(out + threadIdx.x, v);
     }
 }
 
@@ -305,6 +317,11 @@ int risvec_destroy(risvec_env_t* env) {
     cudaSetDevice(env->device);
     if (env->arena) cudaFree(env->arena);
     if (env->stage) cudaFree(env->stage);
+    if (env->pipe_ready) {
+        cudaStreamDestroy(env->s_in);
+        cudaStreamDestroy(env->s_out);
+        for (int i = 0; i < 2 * 16 + 2; ++i) cudaEventDestroy(env->ev[i]);
+    }
     delete env;
     return RISVEC_OK;
 }
@@ -467,27 +484,52 @@ int risvec_rollout_sarl(risvec_env_t* env, int T, const float* action, const flo
     }
 }
 
-// ---- host-buffer variants: H2D staging -> rollout -> D2H of the requested traces
+// ---- host-buffer variants.  The T steps are cut into chunks and pipelined over three streams:
+// chunk c+1 is copied in (H2D engine) while chunk c computes on the caller's stream and
+// chunk c-1 is copied out (D2H engine), so the call runs at PCIe speed of the larger direction.
+namespace {
+
+constexpr int kMaxChunks = 16;
+
+int ensure_pipe(risvec_env* env) {
+    if (env->pipe_ready) return RISVEC_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&env->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&env->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2 * kMaxChunks + 2; ++i)
+        CUDA_TRY(cudaEventCreateWithFlags(&env->ev[i], cudaEventDisableTiming));
+    env->pipe_ready = 1;
+    return RISVEC_OK;
+}
+
+int chunk_steps(int T, size_t in_bytes_per_step) {
+    // ~24 MB of input per chunk, at most kMaxChunks chunks
+    size_t per = (size_t)24 << 20;
+    int tc = (int)(per / (in_bytes_per_step ? in_bytes_per_step : 1));
+    if (tc < 1) tc = 1;
+    int n = (T + tc - 1) / tc;
+    if (n > kMaxChunks) n = kMaxChunks;
+    return (T + n - 1) / n;
+}
+
+}  // namespace
+
 int risvec_rollout_marl_host(risvec_env_t* env, int T, const float* action, const int32_t* partner,
                              const int32_t* ngroups, const int32_t* arrivals, const risvec_marl_out_t* out,
                              void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     if (T < 1 || !action || !partner || !ngroups) return fail(RISVEC_ERR_INVALID, "bad arguments");
     CUDA_TRY(cudaSetDevice(env->device));
+    if (int rc = ensure_pipe(env)) return rc;
     const size_t E = env->dims.E, V = env->dims.V, TE = (size_t)T * E;
     const size_t n_act = TE * 2 * V, n_ev = TE * V;
     size_t need = 256 * 16 + 4 * (n_act + E * V + E + n_ev) + 4 * (6 * n_ev + TE + TE * RISVEC_NSTAT + n_act);
     if (int rc = ensure_stage(env, need)) return rc;
     Carver c{env->stage, 0};
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = (cudaStream_t)stream, si = env->s_in, so = env->s_out;
     float* d_act = c.take<float>(n_act);
     int* d_part = c.take<int>(E * V);
     int* d_ng = c.take<int>(E);
     int* d_arr = arrivals ? c.take<int>(n_ev) : nullptr;
-    CUDA_TRY(cudaMemcpyAsync(d_act, action, n_act * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_part, partner, E * V * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_ng, ngroups, E * 4, cudaMemcpyHostToDevice, st));
-    if (arrivals) CUDA_TRY(cudaMemcpyAsync(d_arr, arrivals, n_ev * 4, cudaMemcpyHostToDevice, st));
     risvec_marl_out_t d_out;
     memset(&d_out, 0, sizeof(d_out));
     risvec_marl_out_t h = out ? *out : d_out;
@@ -500,11 +542,45 @@ int risvec_rollout_marl_host(risvec_env_t* env, int T, const float* action, cons
     if (h.over_power) d_out.over_power = c.take<float>(n_ev);
     if (h.stats) d_out.stats = c.take<float>(TE * RISVEC_NSTAT);
     if (h.last_power) d_out.last_power = c.take<float>(n_act);
-    if (int rc = risvec_rollout_marl(env, T, d_act, d_part, d_ng, d_arr, &d_out, stream)) return rc;
-#define D2H(member, count) \
-    if (h.member) CUDA_TRY(cudaMemcpyAsync(h.member, d_out.member, (count) * 4, cudaMemcpyDeviceToHost, st))
-    D2H(reward_user, n_ev); D2H(reward, TE); D2H(DataBuf, n_ev); D2H(data_t, n_ev); D2H(data_p, n_ev);
-    D2H(rate, n_ev); D2H(over_power, n_ev); D2H(stats, TE * RISVEC_NSTAT); D2H(last_power, n_act);
+
+    cudaEvent_t* ev_in = env->ev;
+    cudaEvent_t* ev_k = env->ev + kMaxChunks;
+    cudaEvent_t ev_start = env->ev[2 * kMaxChunks], ev_done = env->ev[2 * kMaxChunks + 1];
+    CUDA_TRY(cudaEventRecord(ev_start, st));  // staging may still be read by earlier work on `stream`
+    CUDA_TRY(cudaStreamWaitEvent(si, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(so, ev_start, 0));
+    CUDA_TRY(cudaMemcpyAsync(d_part, partner, E * V * 4, cudaMemcpyHostToDevice, si));
+    CUDA_TRY(cudaMemcpyAsync(d_ng, ngroups, E * 4, cudaMemcpyHostToDevice, si));
+    const int Tc = chunk_steps(T, E * (2 * V + V) * 4);
+    int nchunk = 0;
+    for (int t0 = 0; t0 < T; t0 += Tc, ++nchunk) {
+        const size_t n = (size_t)((T - t0 < Tc) ? T - t0 : Tc) * E, o = (size_t)t0 * E;
+        CUDA_TRY(cudaMemcpyAsync(d_act + o * 2 * V, action + o * 2 * V, n * 2 * V * 4, cudaMemcpyHostToDevice, si));
+        if (arrivals) CUDA_TRY(cudaMemcpyAsync(d_arr + o * V, arrivals + o * V, n * V * 4, cudaMemcpyHostToDevice, si));
+        CUDA_TRY(cudaEventRecord(ev_in[nchunk], si));
+    }
+    int ci = 0;
+    for (int t0 = 0; t0 < T; t0 += Tc, ++ci) {
+        const int tn = (T - t0 < Tc) ? T - t0 : Tc;
+        const size_t n = (size_t)tn * E, o = (size_t)t0 * E;
+        CUDA_TRY(cudaStreamWaitEvent(st, ev_in[ci], 0));
+        risvec_marl_out_t oc;
+        memset(&oc, 0, sizeof(oc));
+#define OFF(member, per) oc.member = d_out.member ? d_out.member + o * (per) : nullptr
+        OFF(reward_user, V); OFF(reward, 1); OFF(DataBuf, V); OFF(data_t, V); OFF(data_p, V); OFF(rate, V);
+        OFF(over_power, V); OFF(stats, RISVEC_NSTAT); OFF(last_power, 2 * V);
+        if (int rc = risvec_rollout_marl(env, tn, d_act + o * 2 * V, d_part, d_ng, d_arr ? d_arr + o * V : nullptr, &oc,
+                                         stream))
+            return rc;
+        CUDA_TRY(cudaEventRecord(ev_k[ci], st));
+        CUDA_TRY(cudaStreamWaitEvent(so, ev_k[ci], 0));
+#define D2H(member, per) \
+    if (h.member) CUDA_TRY(cudaMemcpyAsync(h.member + o * (per), oc.member, n * (per) * 4, cudaMemcpyDeviceToHost, so))
+        D2H(reward_user, V); D2H(reward, 1); D2H(DataBuf, V); D2H(data_t, V); D2H(data_p, V); D2H(rate, V);
+        D2H(over_power, V); D2H(stats, RISVEC_NSTAT); D2H(last_power, 2 * V);
+    }
+    CUDA_TRY(cudaEventRecord(ev_done, so));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));  // the caller only has to synchronise `stream`
     return RISVEC_OK;
 }
 
@@ -513,18 +589,16 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     if (T < 1 || !action || !phase) return fail(RISVEC_ERR_INVALID, "bad arguments");
     CUDA_TRY(cudaSetDevice(env->device));
+    if (int rc = ensure_pipe(env)) return rc;
     const size_t E = env->dims.E, V = env->dims.V, M = env->dims.M, TE = (size_t)T * E;
     const size_t n_act = TE * 2 * V, n_ev = TE * V, n_ph = TE * M;
     size_t need = 256 * 16 + 4 * (n_act + n_ph + n_ev) + 4 * (6 * n_ev + TE);
     if (int rc = ensure_stage(env, need)) return rc;
     Carver c{env->stage, 0};
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = (cudaStream_t)stream, si = env->s_in, so = env->s_out;
     float* d_act = c.take<float>(n_act);
     float* d_ph = c.take<float>(n_ph);
     int* d_arr = arrivals ? c.take<int>(n_ev) : nullptr;
-    CUDA_TRY(cudaMemcpyAsync(d_act, action, n_act * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_ph, phase, n_ph * 4, cudaMemcpyHostToDevice, st));
-    if (arrivals) CUDA_TRY(cudaMemcpyAsync(d_arr, arrivals, n_ev * 4, cudaMemcpyHostToDevice, st));
     risvec_sarl_out_t d_out;
     memset(&d_out, 0, sizeof(d_out));
     risvec_sarl_out_t h = out ? *out : d_out;
@@ -535,17 +609,52 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
     if (h.over_power) d_out.over_power = c.take<float>(n_ev);
     if (h.over_data) d_out.over_data = c.take<float>(n_ev);
     if (h.rate) d_out.rate = c.take<float>(n_ev);
-    if (int rc = risvec_rollout_sarl(env, T, d_act, d_ph, d_arr, &d_out, stream)) return rc;
-    D2H(reward, TE); D2H(DataBuf, n_ev); D2H(data_t, n_ev); D2H(data_p, n_ev); D2H(over_power, n_ev);
-    D2H(over_data, n_ev); D2H(rate, n_ev);
+
+    cudaEvent_t* ev_in = env->ev;
+    cudaEvent_t* ev_k = env->ev + kMaxChunks;
+    cudaEvent_t ev_start = env->ev[2 * kMaxChunks], ev_done = env->ev[2 * kMaxChunks + 1];
+    CUDA_TRY(cudaEventRecord(ev_start, st));
+    CUDA_TRY(cudaStreamWaitEvent(si, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(so, ev_start, 0));
+    const int Tc = chunk_steps(T, E * (2 * V + V + M) * 4);
+    int nchunk = 0;
+    for (int t0 = 0; t0 < T; t0 += Tc, ++nchunk) {
+        const size_t n = (size_t)((T - t0 < Tc) ? T - t0 : Tc) * E, o = (size_t)t0 * E;
+        CUDA_TRY(cudaMemcpyAsync(d_act + o * 2 * V, action + o * 2 * V, n * 2 * V * 4, cudaMemcpyHostToDevice, si));
+        CUDA_TRY(cudaMemcpyAsync(d_ph + o * M, phase + o * M, n * M * 4, cudaMemcpyHostToDevice, si));
+        if (arrivals) CUDA_TRY(cudaMemcpyAsync(d_arr + o * V, arrivals + o * V, n * V * 4, cudaMemcpyHostToDevice, si));
+        CUDA_TRY(cudaEventRecord(ev_in[nchunk], si));
+    }
+    int ci = 0;
+    for (int t0 = 0; t0 < T; t0 += Tc, ++ci) {
+        const int tn = (T - t0 < Tc) ? T - t0 : Tc;
+        const size_t n = (size_t)tn * E, o = (size_t)t0 * E;
+        CUDA_TRY(cudaStreamWaitEvent(st, ev_in[ci], 0));
+        risvec_sarl_out_t oc;
+        memset(&oc, 0, sizeof(oc));
+        OFF(reward, 1); OFF(DataBuf, V); OFF(data_t, V); OFF(data_p, V); OFF(over_power, V); OFF(over_data, V);
+        OFF(rate, V);
+        if (int rc = risvec_rollout_sarl(env, tn, d_act + o * 2 * V, d_ph + o * M, d_arr ? d_arr + o * V : nullptr, &oc,
+                                         stream))
+            return rc;
+        CUDA_TRY(cudaEventRecord(ev_k[ci], st));
+        CUDA_TRY(cudaStreamWaitEvent(so, ev_k[ci], 0));
+        D2H(reward, 1); D2H(DataBuf, V); D2H(data_t, V); D2H(data_p, V); D2H(over_power, V); D2H(over_data, V);
+        D2H(rate, V);
+    }
 #undef D2H
+#undef OFF
+    CUDA_TRY(cudaEventRecord(ev_done, so));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));
     return RISVEC_OK;
 }
 
 int risvec_shard_stats(risvec_env_t* env, double* out, void* stream) {
     if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(env->device));
-    k_shard_stats<<<RISVEC_NSTAT + 1, 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
+    CUDA_TRY(cudaMemsetAsync(out, 0, (RISVEC_NSTAT + 1) * sizeof(double), (cudaStream_t)stream));
+    const int blocks = env->dims.E >= 2048 ? 32 : (env->dims.E + 63) / 64;
+    k_shard_stats<<<blocks, 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
     return check_launch(env, "k_shard_stats");
 }
 

@@ -162,3 +162,47 @@ def test_device_poisson_moments():
     assert abs(d.mean().item() - 3.0) < 5 * (3.0 / n) ** 0.5
     assert abs(d.var().item() - 3.0) < 0.1
     assert not torch.equal(draws[0], draws[1])
+
+
+def test_host_pipeline_multi_chunk_and_shard_stats():
+    """4096 envs x 64 steps = several pipeline chunks: the chunked host entry must be bit-identical
+    to one device launch (SARL and MARL), and shard_stats must equal the column sums."""
+    from ris_vec_marl_b200 import BatchedEnviron, encode_groups, marl_yaml_overrides
+
+    E, V, M, T = 4096, 8, 40, 64
+    gen = torch.Generator().manual_seed(11)
+    acts = torch.rand(T, E, 2, V, generator=gen).pin_memory()
+    ph = (torch.rand(T, E, M, generator=gen) * 6.2831853).pin_memory()
+    arr = torch.poisson(torch.full((T, E, V), 2.0), generator=gen).to(torch.int32).pin_memory()
+    # SARL
+    envs = [BatchedEnviron("sarl", E, V, M, seed=5) for _ in range(2)]
+    for e in envs:
+        e.make_new_game(); e.renew_positions(); e.compute_parms()
+    dev = envs[0].rollout_sarl(acts.cuda(), ph.cuda(), arr.cuda())
+    host = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in dev.items()}
+    envs[1].rollout_sarl_host(acts, ph, arr, host)
+    torch.cuda.synchronize()
+    for k in dev:
+        assert torch.equal(dev[k].cpu(), host[k]), k
+    assert torch.equal(envs[0].DataBuf, envs[1].DataBuf)
+    st = envs[0].shard_stats().cpu()
+    assert abs(st[16].item() - envs[0].reward.double().sum().item()) < 1e-6
+    # MARL
+    part, ng = encode_groups([[0, 1], [2, 3], [4, 5], [6], [7]], V)
+    partner = torch.as_tensor(np.tile(part, (E, 1))).pin_memory()
+    ngroups = torch.full((E,), ng, dtype=torch.int32).pin_memory()
+    envs = [BatchedEnviron("marl", E, V, M, seed=6, **marl_yaml_overrides()) for _ in range(2)]
+    for e in envs:
+        e.make_new_game(); e.renew_positions(); e.compute_parms(); e.optimize_phase_shift(); e.update_channel_gains()
+    names = ("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate")
+    dev = envs[0].rollout_marl(acts.cuda(), partner.cuda(), ngroups.cuda(), arr.cuda(), traces=names)
+    host = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in dev.items()}
+    envs[1].rollout_marl_host(acts, partner, ngroups, arr, host)
+    torch.cuda.synchronize()
+    for k in dev:
+        assert torch.equal(dev[k].cpu(), host[k]), k
+    assert torch.equal(envs[0].mec_queue_cycles, envs[1].mec_queue_cycles)
+    st = envs[0].shard_stats().cpu().numpy()
+    want = envs[0].stats.double().sum(dim=0).cpu().numpy()
+    np.testing.assert_allclose(st[:16], want, rtol=1e-12, atol=1e-9)
+    assert abs(st[16] - envs[0].reward.double().sum().item()) < 1e-6

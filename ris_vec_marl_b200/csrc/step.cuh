@@ -452,6 +452,20 @@ __device__ __forceinline__ void sincos_fast2(float2 x, float2* sn, float2* cs) {
     cs->y = __int_as_float(__float_as_int(cb) ^ (((qb + 1) << 30) & 0x80000000));
 }
 
+// ln(1 + x) for x >= 0 through the SFU: MUFU.LG2 of the rounded sum.  Absolute error <= 6e-8 near
+// zero (the rounding of 1 + x) and ~2^-22 relative elsewhere -- inside the SARL rate tolerance
+// (tests/parity.py), and SARL has no threshold on the rate itself.
+__device__ __forceinline__ float log1p_sfu(float x) { return __fmul_rn(__log2f(__fadd_rn(1.0f, x)), 0.693147180559945309f); }
+
+// cbrt(x) for x >= 0: SFU seed exp2(log2(x) / 3) (rel. error ~5e-7) + one Newton step
+// y <- y - (y^3 - x) / (3 y^2), which brings it to ~1 ulp; cbrt(0) = 0.
+__device__ __forceinline__ float cbrt_sfu(float x) {
+    const float y = exp2f(__fmul_rn(__log2f(x), 0.333333343f));
+    const float y2 = __fmul_rn(y, y);
+    const float r = __fdividef(__fmaf_rn(-y2, y, x), __fmul_rn(3.0f, y2));
+    return (x > 0.f) ? __fadd_rn(y, r) : 0.f;
+}
+
 __device__ __forceinline__ float2 shfl_xor2(float2 x, int o) {
     return make_float2(__shfl_xor_sync(kFull, x.x, o), __shfl_xor_sync(kFull, x.y, o));
 }
@@ -577,10 +591,10 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
             sarl_mac(cs.y, sn.y, WX[i], WY[i], RE1, IM1);
         }
         const float g0 = sarl_reduce_abs2(RE0, IM0), g1 = sarl_reduce_abs2(RE1, IM1);
-        h0.rate = log1pf(__fmul_rn(i0.a0, __fmul_rn(coef, g0)));
-        h1.rate = log1pf(__fmul_rn(i1.a0, __fmul_rn(coef, g1)));
-        h0.data_p = __fmul_rn(cbrtf(i0.a1), c_dp);
-        h1.data_p = __fmul_rn(cbrtf(i1.a1), c_dp);
+        h0.rate = log1p_sfu(__fmul_rn(i0.a0, __fmul_rn(coef, g0)));
+        h1.rate = log1p_sfu(__fmul_rn(i1.a0, __fmul_rn(coef, g1)));
+        h0.data_p = __fmul_rn(cbrt_sfu(i0.a1), c_dp);
+        h1.data_p = __fmul_rn(cbrt_sfu(i1.a1), c_dp);
     };
 
     float l_rate = 0.f, l_dt = 0.f, l_dp = 0.f, l_overp = 0.f, l_overd = 0.f, l_rew = 0.f;

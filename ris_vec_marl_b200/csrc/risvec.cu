@@ -63,7 +63,6 @@ struct risvec_env {
     cudaStream_t s_in, s_out;
     cudaEvent_t ev[2 * 16 + 2];
     int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
-    int sarl_ws;        // RISVEC_SARL_WS=0: single-warp k_sarl_v8 for rollouts too (A/B measurements)
 };
 
 namespace {
@@ -139,9 +138,7 @@ int launch_sarl_v8(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     const risvec_sarl_out_t& o = a.out;
     const bool full = a.arrivals && o.reward && o.DataBuf && o.data_t && o.data_p && o.over_power && o.over_data &&
                       o.rate;
-    if (mfull && full && a.T >= 8 && env->sarl_ws)  // warp-specialised pipeline (AUX + MAC warp per 4 envs)
-        k_sarl_ws<MPI><<<warps, 64, 0, st>>>(env->dims, env->st, env->params, a);
-    else if (mfull && full)
+    if (mfull && full)
         k_sarl_v8<MPI, true, true><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
     else if (mfull)
         k_sarl_v8<MPI, true, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
@@ -272,8 +269,6 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
     {
         const char* fg = getenv("RISVEC_FORCE_GENERIC");
         env->force_generic = (fg != nullptr && fg[0] == '1');
-        const char* ws = getenv("RISVEC_SARL_WS");
-        env->sarl_ws = !(ws != nullptr && ws[0] == '0');
     }
     Dims& d = env->dims;
     d.E = E; d.V = V; d.M = M; d.ncand = 1 << control_bit; d.variant = variant;

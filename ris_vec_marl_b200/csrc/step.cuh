@@ -570,10 +570,30 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
         in.arr = (FULL || ar_b != nullptr) ? __ldg(ar_b + (size_t)tc * sV) : 0;
     };
 
-    auto prefetch_l2 = [&](unsigned t) {  // the warp's 640 B phase row + 256 B action row of step t
-        const unsigned tc = min(t, Tm1);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ph_b + (size_t)tc * sM + 8 * (lane >> 3)));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ac_b + (size_t)tc * s2V + ((lane & 8) ? V : 0)));
+    // L2 prefetch of everything the warp reads in step t: its 4 envs' rows are contiguous in each
+    // stream (4*M*4 B of phases, 4*2V*4 B of actions, 4*V*4 B of arrivals); one 32 B sector per lane
+    const int e0 = blockIdx.x * 4;
+    const int n_ph = (4 * M * 4 + 31) / 32, n_ac = (4 * 2 * V * 4 + 31) / 32, n_ar = (4 * V * 4 + 31) / 32;
+    const char* pf_base;
+    size_t pf_stride;
+    bool pf_on = true;
+    if (lane < n_ph) {
+        pf_base = (const char*)(a.phase + (size_t)e0 * M) + 32 * lane;
+        pf_stride = (size_t)sM * 4;
+    } else if (lane < n_ph + n_ac) {
+        pf_base = (const char*)(a.action + (size_t)e0 * 2 * V) + 32 * (lane - n_ph);
+        pf_stride = (size_t)s2V * 4;
+    } else if (lane < n_ph + n_ac + n_ar && (FULL || a.arrivals != nullptr)) {
+        pf_base = (const char*)(a.arrivals + (size_t)e0 * V) + 32 * (lane - n_ph - n_ac);
+        pf_stride = (size_t)sV * 4;
+    } else {
+        pf_base = (const char*)a.phase;
+        pf_stride = 0;
+        pf_on = false;
+    }
+    pf_on = pf_on && (e0 + 4 <= E);  // the last, partial warp simply does not prefetch
+    auto prefetch_l2 = [&](unsigned t) {
+        if (pf_on) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)min(t, Tm1) * pf_stride));
     };
 
     // state-independent part of two steps: theta = exp(j*phase) (packed over the two steps),
@@ -670,238 +690,6 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
 #pragma unroll
         for (int i = 0; i < MPI; ++i)
             if (MFULL || part + 8 * i < M) s.phase_real[(size_t)e * M + part + 8 * i] = __ldg(q + 8 * i);
-    }
-    if (act && T > 0) {
-        s.databuf[ev] = buf;
-        s.rate[ev] = l_rate;
-        s.data_t[ev] = l_dt;
-        s.data_p[ev] = l_dp;
-        s.over_power[ev] = l_overp;
-        s.over_data[ev] = l_overd;
-        s.data_r[ev] = l_arr;
-        if (v == 0) {
-            s.reward[e] = l_rew;
-            s.step_ctr[e] = step0 + T;
-        }
-    }
-}
-
-// -----------------------------------------------------------------------------------------
-// Warp-specialised SARL rollout (same shapes as k_sarl_v8; FULL traces, M = 8 * MPI, T >= 8).
-// At 4096 envs/GPU the single-warp kernel leaves each SM sub-partition with ~1.7 warps, and the
-// 80-register phasor table forbids simply adding warps.  Here a block is TWO warps serving the
-// same 4 envs with different roles, coupled through shared-memory rings + named barriers:
-//   AUX warp  (no table, ~100 regs): streams the inputs, evaluates theta = exp(j*phase) for a
-//             pair of steps (packed sin/cos) into the theta ring, later picks |S_v|^2 out of the
-//             G ring and runs rate / data_p / the DataBuf recursion / reward / all stores;
-//   MAC warp  (table in registers): pulls a pair's theta out of the ring, does the 2 x 80 FFMA2
-//             cascaded MACs + select-free reduce-scatter, pushes |S_v|^2 into the G ring.
-// Rings are 2 pairs deep, so AUX prepares pair p + 1 while MAC works on pair p and AUX scans
-// pair p - 1: twice the warps per scheduler, no duplicated work, no global-memory hand-off.
-// Barrier ids: 1+s FULL_theta[s], 3+s EMPTY_theta[s], 5+s FULL_G[s], 7+s EMPTY_G[s].
-// -----------------------------------------------------------------------------------------
-template <int ID>
-__device__ __forceinline__ void bar_sync64() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
-template <int ID>
-__device__ __forceinline__ void bar_arrive64() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
-
-template <int MPI>
-__global__ void __launch_bounds__(64, 8) k_sarl_ws(Dims d, State s, risvec_params_t p, SarlArgs a) {
-    constexpr int M = 8 * MPI;
-    __shared__ float2 th_ring[2][2][4][M];  // [stage][step of pair][env][element]
-    __shared__ float g_ring[2][2][32];      // [stage][step of pair][lane]
-    const int w = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31, el = lane >> 3, part = lane & 7;
-    const int E = d.E, V = d.V, T = a.T;
-    const int e_raw = blockIdx.x * 4 + el;
-    const bool env_ok = e_raw < E;
-    const int e = min(e_raw, E - 1), v = part, vc = min(v, V - 1);
-    const bool act = env_ok && v < V;
-    const size_t ev = (size_t)e * V + vc;
-    const unsigned P = ((unsigned)T + 1) >> 1;  // pairs; an odd T leaves a dummy second step
-    const unsigned Tm1 = (unsigned)(T - 1);
-
-    if (w == 1) {
-        // ================================ MAC warp ================================
-        float2 WX[MPI][4], WY[MPI][4];
-        {
-            const double my_delta = d.angle_BR - s.angle[ev];
-#pragma unroll
-            for (int sl = 0; sl < 8; ++sl) {
-                const int v2 = sl ^ part;
-                const double dv = __shfl_sync(kFull, my_delta, (lane & ~7) + v2);
-                const bool ok2 = env_ok && v2 < V;
-#pragma unroll
-                for (int i = 0; i < MPI; ++i) {
-                    float re = 0.f, im = 0.f;
-                    if (ok2) phasor_f32((double)(part + 8 * i) * dv, &re, &im);
-                    if (sl & 1) { WX[i][sl >> 1].y = re; WY[i][sl >> 1].y = im; }
-                    else        { WX[i][sl >> 1].x = re; WY[i][sl >> 1].x = im; }
-                }
-            }
-        }
-        auto mac_pair = [&](auto stage_tag, unsigned pr) {
-            constexpr int S = decltype(stage_tag)::value;
-            bar_sync64<1 + S>();  // theta of this pair has landed
-            float2 t0[MPI], t1[MPI];
-#pragma unroll
-            for (int i = 0; i < MPI; ++i) {
-                t0[i] = th_ring[S][0][el][part + 8 * i];
-                t1[i] = th_ring[S][1][el][part + 8 * i];
-            }
-            bar_arrive64<3 + S>();  // theta slot may be refilled
-            float2 RE[4], IM[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) RE[k] = IM[k] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < MPI; ++i) sarl_mac(t0[i].x, t0[i].y, WX[i], WY[i], RE, IM);
-            const float g0 = sarl_reduce_abs2(RE, IM);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) RE[k] = IM[k] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < MPI; ++i) sarl_mac(t1[i].x, t1[i].y, WX[i], WY[i], RE, IM);
-            const float g1 = sarl_reduce_abs2(RE, IM);
-            if (pr >= 2) bar_sync64<7 + S>();  // G slot has been drained
-            g_ring[S][0][lane] = g0;
-            g_ring[S][1][lane] = g1;
-            bar_arrive64<5 + S>();
-        };
-        unsigned pr = 0;
-        for (; pr + 2 <= P; pr += 2) {
-            mac_pair(std::integral_constant<int, 0>{}, pr);
-            mac_pair(std::integral_constant<int, 1>{}, pr + 1);
-        }
-        if (pr < P) mac_pair(std::integral_constant<int, 0>{}, pr);
-        return;
-    }
-
-    // ================================== AUX warp ==================================
-    double buf = s.databuf[ev];
-    const float coef = (float)(s.amp[ev] / (kSigma * kSigma));  // SARL:157-159
-    const long long step0 = s.step_ctr[e];
-    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
-    const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);  // SARL:331
-    const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));        // SARL:318-319
-    const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
-    const float invV = 1.0f / (float)V;
-    const double tf = p.time_fast;
-
-    const unsigned sM = (unsigned)E * M, s2V = (unsigned)E * 2 * V, sV = (unsigned)E * V, sE = (unsigned)E;
-    const float* const ph_b = a.phase + (size_t)e * M + part;
-    const float* const ac_b = a.action + (size_t)e * 2 * V + vc;
-    const int* const ar_b = a.arrivals + ev;
-    float* const o_buf = a.out.DataBuf + ev;
-    float* const o_dt = a.out.data_t + ev;
-    float* const o_dp = a.out.data_p + ev;
-    float* const o_op = a.out.over_power + ev;
-    float* const o_od = a.out.over_data + ev;
-    float* const o_rt = a.out.rate + ev;
-    float* const o_rw = a.out.reward + e;
-
-    auto load_ph = [&](float (&ph)[MPI], unsigned t) {
-        const float* q = ph_b + (size_t)min(t, Tm1) * sM;
-#pragma unroll
-        for (int i = 0; i < MPI; ++i) ph[i] = __ldg(q + 8 * i);
-    };
-    auto load_sc = [&](SarlScalarIn& in, unsigned t) {
-        const unsigned tc = min(t, Tm1);
-        const float* q = ac_b + (size_t)tc * s2V;
-        in.a0 = __ldg(q);
-        in.a1 = __ldg(q + V);
-        in.arr = __ldg(ar_b + (size_t)tc * sV);
-    };
-    auto prefetch_l2 = [&](unsigned t) {
-        const unsigned tc = min(t, Tm1);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ph_b + (size_t)tc * sM + 8 * (lane >> 3)));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ac_b + (size_t)tc * s2V + ((lane & 8) ? V : 0)));
-    };
-    // theta = exp(j*phase) of one pair of steps (packed over the two steps) -> ring stage S
-    auto produce = [&](auto stage_tag, const float (&ph0)[MPI], const float (&ph1)[MPI], unsigned pr) {
-        constexpr int S = decltype(stage_tag)::value;
-        float2 sn[MPI], cs[MPI];
-#pragma unroll
-        for (int i = 0; i < MPI; ++i) sincos_fast2(make_float2(ph0[i], ph1[i]), &sn[i], &cs[i]);
-        if (pr >= 2) bar_sync64<3 + S>();  // MAC has copied the previous content of this slot
-#pragma unroll
-        for (int i = 0; i < MPI; ++i) {
-            th_ring[S][0][el][part + 8 * i] = make_float2(cs[i].x, sn[i].x);
-            th_ring[S][1][el][part + 8 * i] = make_float2(cs[i].y, sn[i].y);
-        }
-        bar_arrive64<1 + S>();
-    };
-
-    float l_rate = 0.f, l_dt = 0.f, l_dp = 0.f, l_overp = 0.f, l_overd = 0.f, l_rew = 0.f;
-    int l_arr = 0;
-    auto scan_step = [&](const SarlScalarIn& in, float g2, unsigned t) {
-        const float rate = log1p_sfu(__fmul_rn(in.a0, __fmul_rn(coef, g2)));  // SARL:159
-        const float data_p = __fmul_rn(cbrt_sfu(in.a1), c_dp);              // SARL:331
-        const float data_t = __fmul_rn(rate, c_dt);
-        const double raw = __dsub_rn(buf, __dadd_rn((double)data_t, (double)data_p));  // SARL:334
-        const bool neg = raw < 0.0;
-        const float b = __fmul_rn((float)fmax(0.0, raw + (double)data_p), c_rev);
-        const float overp = neg ? __fsub_rn(in.a1, __fmul_rn(__fmul_rn(b, b), b)) : 0.f;  // SARL:337
-        const float overd = neg ? (float)(-raw) : 0.f;
-        const double nb = neg ? 0.0 : raw;
-        const float base = __fsub_rn(-__fmul_rn(t1, __fadd_rn(in.a0, in.a1)), __fmul_rn(t2, (float)nb));
-        const float pen = (nb > 0.0) ? pen1 : ((overd > 2.0f) ? pen2 : 0.f);  // SARL:343-352
-        const float rew = __fmul_rn(seg_sum<8>(act ? __fsub_rn(base, pen) : 0.f), invV);
-        buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)in.arr, tf), 1000.0));  // SARL:354-356
-        if (act) {
-            const size_t o = (size_t)t * sV;
-            o_buf[o] = (float)buf;
-            o_dt[o] = data_t;
-            o_dp[o] = data_p;
-            o_op[o] = overp;
-            o_od[o] = overd;
-            o_rt[o] = rate;
-            if (v == 0) o_rw[(size_t)t * sE] = rew;
-        }
-        l_rate = rate; l_dt = data_t; l_dp = data_p; l_overp = overp; l_overd = overd; l_rew = rew; l_arr = in.arr;
-    };
-    // |S|^2 of pair pr out of the G ring, then the sequential part of its (one or two) steps
-    auto consume = [&](auto stage_tag, const SarlScalarIn& i0, const SarlScalarIn& i1, unsigned pr) {
-        constexpr int S = decltype(stage_tag)::value;
-        bar_sync64<5 + S>();
-        const float g0 = g_ring[S][0][lane], g1 = g_ring[S][1][lane];
-        bar_arrive64<7 + S>();
-        scan_step(i0, g0, 2 * pr);
-        if (2 * pr + 1 < (unsigned)T) scan_step(i1, g1, 2 * pr + 1);
-    };
-
-    // pipeline: iteration pr = [request inputs of pair pr+2] [theta of pair pr+1 -> ring] [scan pair pr]
-    float phX0[MPI], phX1[MPI], phY0[MPI], phY1[MPI];
-    SarlScalarIn c0, c1, x0, x1, y0, y1;
-    using S0 = std::integral_constant<int, 0>;
-    using S1 = std::integral_constant<int, 1>;
-    load_ph(phX0, 0); load_ph(phX1, 1);
-    load_sc(c0, 0); load_sc(c1, 1);
-    load_ph(phY0, 2); load_ph(phY1, 3);
-    load_sc(y0, 2); load_sc(y1, 3);
-    produce(S0{}, phX0, phX1, 0);
-    unsigned pr = 0;
-    for (; pr + 2 <= P; pr += 2) {
-        const unsigned t = 2 * pr;
-        // even pair pr: lives in stage 0; pair pr+1 (inputs in Y) -> stage 1; refill X with pair pr+2
-        prefetch_l2(t + 8); prefetch_l2(t + 9);
-        load_ph(phX0, t + 4); load_ph(phX1, t + 5);
-        load_sc(x0, t + 4); load_sc(x1, t + 5);
-        produce(S1{}, phY0, phY1, pr + 1);
-        consume(S0{}, c0, c1, pr);
-        c0 = y0; c1 = y1;
-        // odd pair pr+1: stage 1; pair pr+2 (inputs in X) -> stage 0; refill Y with pair pr+3
-        prefetch_l2(t + 10); prefetch_l2(t + 11);
-        load_ph(phY0, t + 6); load_ph(phY1, t + 7);
-        load_sc(y0, t + 6); load_sc(y1, t + 7);
-        if (pr + 2 < P) produce(S0{}, phX0, phX1, pr + 2);
-        consume(S1{}, c0, c1, pr + 1);
-        c0 = x0; c1 = x1;
-    }
-    if (pr < P) consume(S0{}, c0, c1, pr);  // P odd: the last pair sits in stage 0
-
-    if (env_ok && T > 0) {  // elements_phase_shift_real = the last action_phase (SARL:128)
-        const float* q = ph_b + (size_t)Tm1 * sM;
-#pragma unroll
-        for (int i = 0; i < MPI; ++i) s.phase_real[(size_t)e * M + part + 8 * i] = __ldg(q + 8 * i);
     }
     if (act && T > 0) {
         s.databuf[ev] = buf;

@@ -262,15 +262,23 @@ def main():
     else:
         phases = torch.rand(T, E, M, device=dev, generator=gen) * 6.283185307179586
         trace_names = ("reward", "DataBuf", "data_t", "data_p", "over_power", "over_data", "rate")
-    out = env._alloc_traces(trace_names, T, trace_names)
+    # SARL streams through the library's packed (tiled) records; MARL through the per-array entry
+    # points, which measure faster for its 3-in / 6-out streams
+    packed = wl == "sarl"
     stats_sum = torch.zeros(17, dtype=torch.float64, device=dev)
+    if packed:
+        in_rec = env.pack_inputs(actions, arrivals, phases)
+        out_rec = torch.empty(T, E // 4, 4 * env.packed_out_words(), dtype=torch.float32, device=dev)
+        reward = torch.empty(T, E, dtype=torch.float32, device=dev)
+        del actions, arrivals, phases
 
-    def one_step():
-        if wl == "marl":
+        def one_step():
+            env.rollout_packed(in_rec, out_rec=out_rec, reward=reward)
+    else:
+        out = env._alloc_traces(trace_names, T, trace_names)
+
+        def one_step():
             env.rollout_marl(actions, partner, ngroups, arrivals, out=out)
-        else:
-            env.rollout_sarl(actions, phases, arrivals, out=out)
-
 
     pending = []
 
@@ -332,18 +340,20 @@ def main():
     value = world * E * T * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the public host-buffer API (pinned host in, pinned host out)
-    h_act = actions.cpu().pin_memory()
-    h_arr = arrivals.cpu().pin_memory()
-    h_out = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in out.items()}
-    if wl == "marl":
-        h_part, h_ng = partner.cpu().pin_memory(), ngroups.cpu().pin_memory()
-        run_host = lambda: env.rollout_marl_host(h_act, h_part, h_ng, h_arr, h_out)
-        h2d = h_act.numel() * 4 + h_arr.numel() * 4 + h_part.numel() * 4 + h_ng.numel() * 4
+    if packed:
+        h_in = in_rec.cpu().pin_memory()
+        h_out = torch.empty(out_rec.shape, dtype=torch.float32).pin_memory()
+        h_rew = torch.empty(reward.shape, dtype=torch.float32).pin_memory()
+        run_host = lambda: env.rollout_packed_host(h_in, h_out, h_rew)
+        h2d, d2h = h_in.numel() * 4, h_out.numel() * 4 + h_rew.numel() * 4
     else:
-        h_ph = phases.cpu().pin_memory()
-        run_host = lambda: env.rollout_sarl_host(h_act, h_ph, h_arr, h_out)
-        h2d = h_act.numel() * 4 + h_arr.numel() * 4 + h_ph.numel() * 4
-    d2h = sum(v.numel() * 4 for v in h_out.values())
+        h_act, h_arr = actions.cpu().pin_memory(), arrivals.cpu().pin_memory()
+        h_part, h_ng = partner.cpu().pin_memory(), ngroups.cpu().pin_memory()
+        h_o = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in out.items()}
+        h_rew = h_o["reward"]
+        run_host = lambda: env.rollout_marl_host(h_act, h_part, h_ng, h_arr, h_o)
+        h2d = (h_act.numel() + h_arr.numel() + h_part.numel() + h_ng.numel()) * 4
+        d2h = sum(v.numel() * 4 for v in h_o.values())
     run_host(); torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -352,7 +362,7 @@ def main():
     for _ in range(args.e2e_steps):
         run_host()
         torch.cuda.current_stream().synchronize()  # the caller reads the step's result on the host
-        _ = float(h_out["reward"][-1, 0])
+        _ = float(h_rew[-1, 0])
     e1.record()
     torch.cuda.synchronize()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

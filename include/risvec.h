@@ -195,6 +195,34 @@ int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int
 int risvec_rollout_sarl(risvec_env_t* env, int T, const float* action, const float* phase, const int32_t* arrivals,
                         const risvec_sarl_out_t* out, void* stream);
 
+/* Packed (tiled) record layout -- the library's native streaming format for the BASELINE shapes
+ * (V == 8 vehicles, E a multiple of 4; SARL additionally M in {16, 40}).  Envs are taken in
+ * groups of 4 (= one warp); per step and group there is ONE input tile and ONE output tile whose
+ * fields are each [4 envs][8 vehicles] = one 128-byte line, so a rollout reads one stream and
+ * writes one stream (+ the per-env reward), every access is a full line, and all fields of a
+ * lane sit at compile-time offsets from one base pointer:
+ *   SARL in  [T, E/4, 4*(24+M)] words: action_power[0] [4][8] f32 | action_power[1] [4][8] f32 |
+ *                                      arrivals [4][8] i32 | action_phase [4][M] f32 (radians)
+ *   SARL out [T, E/4, 4*48] f32: DataBuf | data_t | data_p | over_power | over_data | rate, each [4][8]
+ *   MARL in  [T, E/4, 4*24] words: action_power[0] [4][8] | action_power[1] [4][8] | arrivals [4][8] i32
+ *   MARL out [T, E/4, 4*40] f32: reward_user | DataBuf | data_t | data_p | rate, each [4][8]
+ *   reward   [T, E] f32 (mean / global reward), a separate array in both variants.
+ * Same arithmetic, bit-identical results to the per-array entry points.  Other shapes return
+ * RISVEC_ERR_UNSUPPORTED (use the per-array entry points). */
+#define RISVEC_SARL_IN_WORDS(M) (24 + (M))
+#define RISVEC_SARL_OUT_WORDS 48
+#define RISVEC_MARL_IN_WORDS 24
+#define RISVEC_MARL_OUT_WORDS 40
+int risvec_rollout_sarl_packed(risvec_env_t* env, int T, const void* in_rec, float* out_rec, float* reward,
+                               void* stream);
+int risvec_rollout_marl_packed(risvec_env_t* env, int T, const void* in_rec, const int32_t* partner,
+                               const int32_t* ngroups, float* out_rec, float* reward, void* stream);
+/* ... and with (pinned) HOST records: chunked H2D -> rollout -> D2H pipeline on three streams */
+int risvec_rollout_sarl_packed_host(risvec_env_t* env, int T, const void* in_rec, float* out_rec, float* reward,
+                                    void* stream);
+int risvec_rollout_marl_packed_host(risvec_env_t* env, int T, const void* in_rec, const int32_t* partner,
+                                    const int32_t* ngroups, float* out_rec, float* reward, void* stream);
+
 /* Same two calls with HOST buffers (pinned for full PCIe speed): inputs are copied to device
  * staging owned by the handle, the rollout runs, the non-NULL traces are copied back.  All on
  * `stream`; the caller synchronises the stream before reading the outputs. */

@@ -25,6 +25,16 @@ PARTNER_SINGLE, PARTNER_NONE, PARTNER_SECOND = -1, -2, 1 << 16
 VARIANT = {"marl": 0, "sarl": 1}
 CHANNEL = {"free": 0, "3gpp_umi": 1, "3gpp_uma": 2}
 
+# packed record layout (include/risvec.h): words per (step, env) record, field order of the outputs
+SARL_OUT_WORDS, MARL_IN_WORDS, MARL_OUT_WORDS = 48, 24, 40
+SARL_OUT_FIELDS = ("DataBuf", "data_t", "data_p", "over_power", "over_data", "rate")
+MARL_OUT_FIELDS = ("reward_user", "DataBuf", "data_t", "data_p", "rate")
+
+
+def sarl_in_words(M):
+    return 24 + M
+
+
 STAT_COLUMNS = ("delay_mean", "energy_mean", "delay_local_mean", "delay_edge_q_mean", "delay_edge_c_mean",
                 "t_tx_mean", "backlog_kbit_mean", "mec_utilization", "local_util_mean", "qos_violation",
                 "off_kbit_sum", "local_kbit_sum", "mec_queue_cycles")
@@ -101,6 +111,13 @@ EXPORTS = {
                                            C.POINTER(MarlOut), C.c_void_p]),
     "risvec_rollout_sarl_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(SarlOut), C.c_void_p]),
+    "risvec_rollout_sarl_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "risvec_rollout_marl_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]),
+    "risvec_rollout_sarl_packed_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p]),
+    "risvec_rollout_marl_packed_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_shard_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_launch_count": (C.c_int64, [C.c_void_p]),
 }

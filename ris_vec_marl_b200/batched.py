@@ -266,6 +266,65 @@ class BatchedEnviron:
         check(self._lib.risvec_rollout_marl_host(self._h, T, self._hp(actions), self._hp(partner), self._hp(ngroups),
                                                  self._hp(arrivals), C.byref(o), self.stream))
 
+    # ---- packed record layout: the native streaming format for V == 8 (include/risvec.h)
+    def pack_inputs(self, actions, arrivals, phases=None):
+        """[T,E,2,8] f32 actions, [T,E,8] i32 arrivals (+ [T,E,M] f32 phases for SARL) -> the tiled
+        record tensor [T, E/4, 4*W] f32 (arrivals bit-cast into their words).  Any device."""
+        a = torch.as_tensor(actions, dtype=torch.float32)
+        T, E = a.shape[0], a.shape[1]
+        if E % 4 or a.shape[3] != 8:
+            raise ValueError("packed records need E % 4 == 0 and V == 8")
+        G = E // 4
+        arr = torch.as_tensor(arrivals, dtype=torch.int32).to(a.device).view(torch.float32)
+        parts = [a[:, :, 0, :].reshape(T, G, 32), a[:, :, 1, :].reshape(T, G, 32), arr.reshape(T, G, 32)]
+        if self.variant == "sarl":
+            parts.append(torch.as_tensor(phases, dtype=torch.float32).to(a.device).reshape(T, G, 4 * self.M))
+        return torch.cat(parts, dim=2).contiguous()
+
+    def unpack_outputs(self, out_rec, reward):
+        """[T, E/4, 4*W] output tiles -> {trace: [T,E,8]} (+ reward), names as the per-array API."""
+        names = _lib.SARL_OUT_FIELDS if self.variant == "sarl" else _lib.MARL_OUT_FIELDS
+        T, G = out_rec.shape[0], out_rec.shape[1]
+        d = {n: out_rec[:, :, 32 * i:32 * i + 32].reshape(T, G * 4, 8) for i, n in enumerate(names)}
+        d["reward"] = reward
+        return d
+
+    def packed_out_words(self):
+        return _lib.SARL_OUT_WORDS if self.variant == "sarl" else _lib.MARL_OUT_WORDS
+
+    def rollout_packed(self, in_rec, partner=None, ngroups=None, out_rec=None, reward=None):
+        """One fused rollout on device-resident packed records; returns (out_rec, reward)."""
+        rec = self._dev(in_rec, torch.float32)
+        T = rec.shape[0]
+        if out_rec is None:
+            out_rec = torch.empty(T, self.E // 4, 4 * self.packed_out_words(), dtype=torch.float32, device=self.device)
+        if reward is None:
+            reward = torch.empty(T, self.E, dtype=torch.float32, device=self.device)
+        if self.variant == "sarl":
+            if rec.numel() != T * self.E * _lib.sarl_in_words(self.M):
+                raise ValueError("SARL input tiles must be [T,E/4,4*(24+M)]")
+            check(self._lib.risvec_rollout_sarl_packed(self._h, T, self._p(rec), self._p(out_rec), self._p(reward),
+                                                       self.stream))
+        else:
+            if rec.numel() != T * self.E * _lib.MARL_IN_WORDS:
+                raise ValueError("MARL input tiles must be [T,E/4,4*24]")
+            pt = self._dev(partner, torch.int32, (self.E, self.V))
+            ng = self._dev(ngroups, torch.int32, (self.E,))
+            check(self._lib.risvec_rollout_marl_packed(self._h, T, self._p(rec), self._p(pt), self._p(ng),
+                                                       self._p(out_rec), self._p(reward), self.stream))
+        return out_rec, reward
+
+    def rollout_packed_host(self, in_rec, out_rec, reward, partner=None, ngroups=None):
+        """Same with (pinned) HOST record tensors: chunked H2D -> rollout -> D2H pipeline."""
+        T = in_rec.shape[0]
+        if self.variant == "sarl":
+            check(self._lib.risvec_rollout_sarl_packed_host(self._h, T, self._hp(in_rec), self._hp(out_rec),
+                                                            self._hp(reward), self.stream))
+        else:
+            check(self._lib.risvec_rollout_marl_packed_host(self._h, T, self._hp(in_rec), self._hp(partner),
+                                                            self._hp(ngroups), self._hp(out_rec), self._hp(reward),
+                                                            self.stream))
+
     # ------------------------------------------------------------------ stats / checkpoint
     def last_stats(self):
         """{name: tensor [E]} of the reference's `last_*` attributes after the latest step."""

@@ -138,12 +138,14 @@ int launch_sarl_v8(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     const risvec_sarl_out_t& o = a.out;
     const bool full = a.arrivals && o.reward && o.DataBuf && o.data_t && o.data_p && o.over_power && o.over_data &&
                       o.rate;
-    if (mfull && full)
-        k_sarl_v8<MPI, true, true><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+    if (a.in_rec != nullptr)  // packed records (caller guarantees V == 8, M == 8 * MPI)
+        k_sarl_v8<MPI, true, true, true><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+    else if (mfull && full)
+        k_sarl_v8<MPI, true, true, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
     else if (mfull)
-        k_sarl_v8<MPI, true, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+        k_sarl_v8<MPI, true, false, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
     else
-        k_sarl_v8<MPI, false, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+        k_sarl_v8<MPI, false, false, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
     return check_launch(env, "k_sarl_v8");
 }
 
@@ -447,9 +449,9 @@ int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int
                           !o.over_power;
         const int warps = (env->dims.E + 3) / 4;
         if (full)
-            k_marl_v8<true><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+            k_marl_v8<true, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
         else
-            k_marl_v8<false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
+            k_marl_v8<false, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
         return check_launch(env, "k_marl_v8");
     }
     switch (pow2ceil(env->dims.V)) {
@@ -482,6 +484,50 @@ int risvec_rollout_sarl(risvec_env_t* env, int T, const float* action, const flo
         case 16: return launch_sarl<16>(env, a, st);
         default: return launch_sarl<32>(env, a, st);
     }
+}
+
+// ---- packed record layout (include/risvec.h): one input / one output stream per rollout
+namespace {
+int packed_sarl_mpi(const risvec_env* env) {  // 0 = shape not covered by the packed kernels
+    const int V = env->dims.V, M = env->dims.M;
+    if (V != 8 || env->dims.E % 4 != 0) return 0;
+    return M == 16 ? 2 : (M == 40 ? 5 : 0);
+}
+}  // namespace
+
+int risvec_rollout_sarl_packed(risvec_env_t* env, int T, const void* in_rec, float* out_rec, float* reward,
+                               void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (env->dims.variant != RISVEC_VARIANT_SARL) return fail(RISVEC_ERR_INVALID, "handle is not a SARL env");
+    if (T < 1 || !in_rec || !out_rec || !reward) return fail(RISVEC_ERR_INVALID, "T >= 1 and all three buffers are required");
+    const int mpi = packed_sarl_mpi(env);
+    if (!mpi)
+        return fail(RISVEC_ERR_UNSUPPORTED, "packed SARL records need V == 8, E %% 4 == 0 and M in {16, 40} "
+                    "(got V = %d, E = %d, M = %d)", env->dims.V, env->dims.E, env->dims.M);
+    CUDA_TRY(cudaSetDevice(env->device));
+    SarlArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = T; a.in_rec = (const float*)in_rec; a.out_rec = out_rec; a.out.reward = reward;
+    return mpi == 2 ? launch_sarl_v8<2>(env, a, (cudaStream_t)stream) : launch_sarl_v8<5>(env, a, (cudaStream_t)stream);
+}
+
+int risvec_rollout_marl_packed(risvec_env_t* env, int T, const void* in_rec, const int32_t* partner,
+                               const int32_t* ngroups, float* out_rec, float* reward, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (env->dims.variant != RISVEC_VARIANT_MARL) return fail(RISVEC_ERR_INVALID, "handle is not a MARL env");
+    if (T < 1 || !in_rec || !partner || !ngroups || !out_rec || !reward)
+        return fail(RISVEC_ERR_INVALID, "T >= 1 and all buffers are required");
+    if (env->dims.V != 8 || env->dims.E % 4 != 0)
+        return fail(RISVEC_ERR_UNSUPPORTED, "packed MARL records need V == 8 and E %% 4 == 0 (got V = %d, E = %d)",
+                    env->dims.V, env->dims.E);
+    CUDA_TRY(cudaSetDevice(env->device));
+    MarlArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = T; a.in_rec = (const float*)in_rec; a.partner = partner; a.ngroups = ngroups; a.out_rec = out_rec;
+    a.out.reward = reward;
+    const int warps = (env->dims.E + 3) / 4;
+    k_marl_v8<true, true><<<warps, 32, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, a);
+    return check_launch(env, "k_marl_v8");
 }
 
 // ---- host-buffer variants.  The T steps are cut into chunks and pipelined over three streams:
@@ -647,6 +693,94 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
     CUDA_TRY(cudaEventRecord(ev_done, so));
     CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));
     return RISVEC_OK;
+}
+
+}  // extern "C"
+
+// packed host pipeline shared by both variants: records in, records + reward out
+namespace {
+template <typename Launch>
+int packed_host_pipeline(risvec_env* env, int T, size_t in_words, size_t out_words, const void* in_rec, float* out_rec,
+                         float* reward, size_t extra_dev_bytes, char** extra_dev, void* stream, Launch launch) {
+    if (int rc = ensure_pipe(env)) return rc;
+    const size_t E = env->dims.E, TE = (size_t)T * E;
+    const size_t need = 256 * 8 + 4 * TE * (in_words + out_words + 1) + extra_dev_bytes;
+    if (int rc = ensure_stage(env, need)) return rc;
+    Carver c{env->stage, 0};
+    float* d_in = c.take<float>(TE * in_words);
+    float* d_out = c.take<float>(TE * out_words);
+    float* d_rew = c.take<float>(TE);
+    *extra_dev = extra_dev_bytes ? (char*)c.take<char>(extra_dev_bytes) : nullptr;
+    cudaStream_t st = (cudaStream_t)stream, si = env->s_in, so = env->s_out;
+    cudaEvent_t* ev_in = env->ev;
+    cudaEvent_t* ev_k = env->ev + kMaxChunks;
+    cudaEvent_t ev_start = env->ev[2 * kMaxChunks], ev_done = env->ev[2 * kMaxChunks + 1];
+    CUDA_TRY(cudaEventRecord(ev_start, st));
+    CUDA_TRY(cudaStreamWaitEvent(si, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(so, ev_start, 0));
+    const int Tc = chunk_steps(T, E * in_words * 4);
+    int n = 0;
+    for (int t0 = 0; t0 < T; t0 += Tc, ++n) {
+        const size_t cnt = (size_t)((T - t0 < Tc) ? T - t0 : Tc) * E * in_words, o = (size_t)t0 * E * in_words;
+        CUDA_TRY(cudaMemcpyAsync(d_in + o, (const float*)in_rec + o, cnt * 4, cudaMemcpyHostToDevice, si));
+        CUDA_TRY(cudaEventRecord(ev_in[n], si));
+    }
+    int ci = 0;
+    for (int t0 = 0; t0 < T; t0 += Tc, ++ci) {
+        const int tn = (T - t0 < Tc) ? T - t0 : Tc;
+        const size_t o = (size_t)t0 * E;
+        CUDA_TRY(cudaStreamWaitEvent(st, ev_in[ci], 0));
+        if (int rc = launch(tn, d_in + o * in_words, d_out + o * out_words, d_rew + o)) return rc;
+        CUDA_TRY(cudaEventRecord(ev_k[ci], st));
+        CUDA_TRY(cudaStreamWaitEvent(so, ev_k[ci], 0));
+        CUDA_TRY(cudaMemcpyAsync(out_rec + o * out_words, d_out + o * out_words, (size_t)tn * E * out_words * 4,
+                                 cudaMemcpyDeviceToHost, so));
+        CUDA_TRY(cudaMemcpyAsync(reward + o, d_rew + o, (size_t)tn * E * 4, cudaMemcpyDeviceToHost, so));
+    }
+    CUDA_TRY(cudaEventRecord(ev_done, so));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));
+    return RISVEC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int risvec_rollout_sarl_packed_host(risvec_env_t* env, int T, const void* in_rec, float* out_rec, float* reward,
+                                    void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (T < 1 || !in_rec || !out_rec || !reward) return fail(RISVEC_ERR_INVALID, "bad arguments");
+    if (!packed_sarl_mpi(env))
+        return fail(RISVEC_ERR_UNSUPPORTED, "packed SARL records need V == 8, E %% 4 == 0 and M in {16, 40}");
+    CUDA_TRY(cudaSetDevice(env->device));
+    char* extra = nullptr;
+    return packed_host_pipeline(env, T, RISVEC_SARL_IN_WORDS(env->dims.M), RISVEC_SARL_OUT_WORDS, in_rec, out_rec, reward,
+                                0, &extra, stream, [&](int tn, const float* di, float* dout, float* dr) {
+                                    return risvec_rollout_sarl_packed(env, tn, di, dout, dr, stream);
+                                });
+}
+
+int risvec_rollout_marl_packed_host(risvec_env_t* env, int T, const void* in_rec, const int32_t* partner,
+                                    const int32_t* ngroups, float* out_rec, float* reward, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (T < 1 || !in_rec || !partner || !ngroups || !out_rec || !reward) return fail(RISVEC_ERR_INVALID, "bad arguments");
+    if (env->dims.V != 8 || env->dims.E % 4 != 0)
+        return fail(RISVEC_ERR_UNSUPPORTED, "packed MARL records need V == 8 and E %% 4 == 0");
+    CUDA_TRY(cudaSetDevice(env->device));
+    if (int rc = ensure_pipe(env)) return rc;
+    const size_t E = env->dims.E;
+    char* extra = nullptr;
+    bool copied = false;
+    return packed_host_pipeline(env, T, RISVEC_MARL_IN_WORDS, RISVEC_MARL_OUT_WORDS, in_rec, out_rec, reward,
+                                (E * 8 + E) * 4 + 256, &extra, stream, [&](int tn, const float* di, float* dout, float* dr) {
+                                    int* d_part = (int*)extra;
+                                    int* d_ng = d_part + ((E * 8 + 63) / 64) * 64;
+                                    if (!copied) {  // small per-rollout tables, on the compute stream
+                                        cudaMemcpyAsync(d_part, partner, E * 8 * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+                                        cudaMemcpyAsync(d_ng, ngroups, E * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+                                        copied = true;
+                                    }
+                                    return risvec_rollout_marl_packed(env, tn, di, d_part, d_ng, dout, dr, stream);
+                                });
 }
 
 int risvec_shard_stats(risvec_env_t* env, double* out, void* stream) {

@@ -21,6 +21,8 @@ struct MarlArgs {
     const int* ngroups;    // [E]
     const int* arrivals;   // [T,E,V] or null
     risvec_marl_out_t out;
+    const float* in_rec;   // packed layout: [T,E,RISVEC_MARL_IN_WORDS]  (see include/risvec.h)
+    float* out_rec;        // packed layout: [T,E,RISVEC_MARL_OUT_WORDS]
 };
 
 struct SarlArgs {
@@ -29,6 +31,8 @@ struct SarlArgs {
     const float* phase;   // [T,E,M]
     const int* arrivals;  // [T,E,V] or null
     risvec_sarl_out_t out;
+    const float* in_rec;  // packed layout: [T,E,24 + M]  (see include/risvec.h)
+    float* out_rec;       // packed layout: [T,E,RISVEC_SARL_OUT_WORDS]
 };
 
 __device__ inline int draw_arrival(const Dims& d, int e, int v, long long step, float lam) {
@@ -502,8 +506,11 @@ struct SarlHeavyOut {  // state-independent results of a step
     float rate, data_p;
 };
 
-template <int MPI, bool MFULL, bool FULL>
+template <int MPI, bool MFULL, bool FULL, bool PACKED>
 __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t p, SarlArgs a) {
+    static_assert(!PACKED || (MFULL && FULL), "the packed record layout carries every stream");
+    constexpr int RIN = 24 + 8 * MPI;            // packed input record (words): a0[8] a1[8] arr[8] phase[M]
+    constexpr int ROUT = RISVEC_SARL_OUT_WORDS;  // packed output record: six traces x 8 vehicles
     const int lane = threadIdx.x & 31, el = lane >> 3, part = lane & 7;
     const int E = d.E, V = d.V, M = d.M, T = a.T;
     const int e_raw = blockIdx.x * 4 + el;
@@ -544,52 +551,76 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
 
     // ---- per-lane stream bases; step t of a stream sits t * (warp-uniform 32-bit stride) further
     // (the host checks that every stride fits 32 bits; the product is formed in 64 bits)
+    // PACKED: one input and one output record per (step, env); every field of a lane sits at a
+    // compile-time offset from ONE base pointer per direction, so a step costs two pointer bumps
+    // instead of ten 64-bit address computations.
     const unsigned sM = (unsigned)E * M, s2V = (unsigned)E * 2 * V, sV = (unsigned)E * V, sE = (unsigned)E;
-    const float* const ph_b = a.phase + (size_t)e * M + part;
-    const float* const ac_b = a.action + (size_t)e * 2 * V + vc;
-    const int* const ar_b = (FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr;
-    float* const o_buf = a.out.DataBuf ? a.out.DataBuf + ev : nullptr;
-    float* const o_dt = a.out.data_t ? a.out.data_t + ev : nullptr;
-    float* const o_dp = a.out.data_p ? a.out.data_p + ev : nullptr;
-    float* const o_op = a.out.over_power ? a.out.over_power + ev : nullptr;
-    float* const o_od = a.out.over_data ? a.out.over_data + ev : nullptr;
-    float* const o_rt = a.out.rate ? a.out.rate + ev : nullptr;
+    const unsigned sIn = (unsigned)E * RIN, sOut = (unsigned)E * ROUT;
+    // (records are tiled per warp: for each field the 4 envs x 8 vehicles of a warp are one
+    //  contiguous 128 B line, so every load/store instruction still covers whole lines)
+    const size_t grp = blockIdx.x;
+    const float* const in_b = PACKED ? a.in_rec + grp * (4 * RIN) + el * 8 + part : nullptr;
+    float* const out_b = PACKED ? a.out_rec + grp * (4 * ROUT) + el * 8 + part : nullptr;
+    const float* const ph_b = PACKED ? a.in_rec + grp * (4 * RIN) + 96 + el * (8 * MPI) + part
+                                     : a.phase + (size_t)e * M + part;
+    const float* const ac_b = PACKED ? in_b : a.action + (size_t)e * 2 * V + vc;
+    const int* const ar_b = PACKED ? nullptr : ((FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr);
+    float* const o_buf = (!PACKED && a.out.DataBuf) ? a.out.DataBuf + ev : nullptr;
+    float* const o_dt = (!PACKED && a.out.data_t) ? a.out.data_t + ev : nullptr;
+    float* const o_dp = (!PACKED && a.out.data_p) ? a.out.data_p + ev : nullptr;
+    float* const o_op = (!PACKED && a.out.over_power) ? a.out.over_power + ev : nullptr;
+    float* const o_od = (!PACKED && a.out.over_data) ? a.out.over_data + ev : nullptr;
+    float* const o_rt = (!PACKED && a.out.rate) ? a.out.rate + ev : nullptr;
     float* const o_rw = a.out.reward ? a.out.reward + e : nullptr;
     const unsigned Tm1 = (unsigned)(T - 1);
 
     auto load_ph = [&](float (&ph)[MPI], unsigned t) {
-        const float* q = ph_b + (size_t)min(t, Tm1) * sM;
+        const float* q = ph_b + (size_t)min(t, Tm1) * (PACKED ? sIn : sM);
 #pragma unroll
         for (int i = 0; i < MPI; ++i) ph[i] = (MFULL || part + 8 * i < M) ? __ldg(q + 8 * i) : 0.f;
     };
     auto load_sc = [&](SarlScalarIn& in, unsigned t) {
         const unsigned tc = min(t, Tm1);
-        const float* q = ac_b + (size_t)tc * s2V;
-        in.a0 = __ldg(q);
-        in.a1 = __ldg(q + V);
-        in.arr = (FULL || ar_b != nullptr) ? __ldg(ar_b + (size_t)tc * sV) : 0;
+        if constexpr (PACKED) {
+            const float* q = in_b + (size_t)tc * sIn;
+            in.a0 = __ldg(q);
+            in.a1 = __ldg(q + 32);
+            in.arr = __ldg(reinterpret_cast<const int*>(q) + 64);
+        } else {
+            const float* q = ac_b + (size_t)tc * s2V;
+            in.a0 = __ldg(q);
+            in.a1 = __ldg(q + V);
+            in.arr = (FULL || ar_b != nullptr) ? __ldg(ar_b + (size_t)tc * sV) : 0;
+        }
     };
 
     // L2 prefetch of everything the warp reads in step t: its 4 envs' rows are contiguous in each
-    // stream (4*M*4 B of phases, 4*2V*4 B of actions, 4*V*4 B of arrivals); one 32 B sector per lane
+    // stream (PACKED: one 4*RIN*4 B slab; else 4*M*4 B of phases, 4*2V*4 B of actions, 4*V*4 B of
+    // arrivals); one 32 B sector per lane
     const int e0 = blockIdx.x * 4;
-    const int n_ph = (4 * M * 4 + 31) / 32, n_ac = (4 * 2 * V * 4 + 31) / 32, n_ar = (4 * V * 4 + 31) / 32;
     const char* pf_base;
     size_t pf_stride;
     bool pf_on = true;
-    if (lane < n_ph) {
-        pf_base = (const char*)(a.phase + (size_t)e0 * M) + 32 * lane;
-        pf_stride = (size_t)sM * 4;
-    } else if (lane < n_ph + n_ac) {
-        pf_base = (const char*)(a.action + (size_t)e0 * 2 * V) + 32 * (lane - n_ph);
-        pf_stride = (size_t)s2V * 4;
-    } else if (lane < n_ph + n_ac + n_ar && (FULL || a.arrivals != nullptr)) {
-        pf_base = (const char*)(a.arrivals + (size_t)e0 * V) + 32 * (lane - n_ph - n_ac);
-        pf_stride = (size_t)sV * 4;
+    if constexpr (PACKED) {
+        pf_base = (const char*)(a.in_rec + grp * (4 * RIN)) + 32 * lane;
+        pf_stride = (size_t)sIn * 4;
+        pf_on = lane < (4 * RIN * 4 + 31) / 32;
     } else {
-        pf_base = (const char*)a.phase;
-        pf_stride = 0;
-        pf_on = false;
+        const int n_ph = (4 * M * 4 + 31) / 32, n_ac = (4 * 2 * V * 4 + 31) / 32, n_ar = (4 * V * 4 + 31) / 32;
+        if (lane < n_ph) {
+            pf_base = (const char*)(a.phase + (size_t)e0 * M) + 32 * lane;
+            pf_stride = (size_t)sM * 4;
+        } else if (lane < n_ph + n_ac) {
+            pf_base = (const char*)(a.action + (size_t)e0 * 2 * V) + 32 * (lane - n_ph);
+            pf_stride = (size_t)s2V * 4;
+        } else if (lane < n_ph + n_ac + n_ar && (FULL || a.arrivals != nullptr)) {
+            pf_base = (const char*)(a.arrivals + (size_t)e0 * V) + 32 * (lane - n_ph - n_ac);
+            pf_stride = (size_t)sV * 4;
+        } else {
+            pf_base = (const char*)a.phase;
+            pf_stride = 0;
+            pf_on = false;
+        }
     }
     pf_on = pf_on && (e0 + 4 <= E);  // the last, partial warp simply does not prefetch
     auto prefetch_l2 = [&](unsigned t) {
@@ -640,13 +671,18 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
         const float rew = __fmul_rn(seg_sum<8>(act ? ru : 0.f), invV);
         buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, tf), 1000.0));  // SARL:354-356
         if (act) {
-            const size_t o = (size_t)t * sV;
-            if (FULL || o_buf) o_buf[o] = (float)buf;
-            if (FULL || o_dt) o_dt[o] = data_t;
-            if (FULL || o_dp) o_dp[o] = h.data_p;
-            if (FULL || o_op) o_op[o] = overp;
-            if (FULL || o_od) o_od[o] = overd;
-            if (FULL || o_rt) o_rt[o] = h.rate;
+            if constexpr (PACKED) {
+                float* q = out_b + (size_t)t * sOut;
+                q[0] = (float)buf; q[32] = data_t; q[64] = h.data_p; q[96] = overp; q[128] = overd; q[160] = h.rate;
+            } else {
+                const size_t o = (size_t)t * sV;
+                if (FULL || o_buf) o_buf[o] = (float)buf;
+                if (FULL || o_dt) o_dt[o] = data_t;
+                if (FULL || o_dp) o_dp[o] = h.data_p;
+                if (FULL || o_op) o_op[o] = overp;
+                if (FULL || o_od) o_od[o] = overd;
+                if (FULL || o_rt) o_rt[o] = h.rate;
+            }
             if (v == 0 && (FULL || o_rw)) o_rw[(size_t)t * sE] = rew;
         }
         l_rate = h.rate; l_dt = data_t; l_dp = h.data_p; l_overp = overp; l_overd = overd; l_rew = rew; l_arr = arr;
@@ -686,7 +722,7 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
     if (T & 1) scan_step(c0, h0, Tm1);
 
     if (env_ok && T > 0) {  // elements_phase_shift_real = the last action_phase (SARL:128)
-        const float* q = ph_b + (size_t)Tm1 * sM;
+        const float* q = ph_b + (size_t)Tm1 * (PACKED ? sIn : sM);
 #pragma unroll
         for (int i = 0; i < MPI; ++i)
             if (MFULL || part + 8 * i < M) s.phase_real[(size_t)e * M + part + 8 * i] = __ldg(q + 8 * i);
@@ -724,8 +760,10 @@ struct MarlHeavy {
     double f_local, cap;
 };
 
-template <bool FULL>
+template <bool FULL, bool PACKED>
 __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t p, MarlArgs a) {
+    static_assert(!PACKED || FULL, "the packed record layout carries every stream");
+    constexpr int RIN = RISVEC_MARL_IN_WORDS, ROUT = RISVEC_MARL_OUT_WORDS;
     const int lane = threadIdx.x & 31, el = lane >> 3, v = lane & 7;
     const int E = d.E, V = d.V, T = a.T;
     const int e_raw = blockIdx.x * 4 + el;
@@ -775,23 +813,34 @@ __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t
     const float lam = (float)p.rate;
 
     const unsigned s2V = (unsigned)E * 2 * V, sV = (unsigned)E * V, sE = (unsigned)E;
-    const float* const ac_b = a.action + (size_t)e * 2 * V + vc;
-    const int* const ar_b = (FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr;
-    float* const o_ru = a.out.reward_user ? a.out.reward_user + ev : nullptr;
-    float* const o_buf = a.out.DataBuf ? a.out.DataBuf + ev : nullptr;
-    float* const o_dt = a.out.data_t ? a.out.data_t + ev : nullptr;
-    float* const o_dp = a.out.data_p ? a.out.data_p + ev : nullptr;
-    float* const o_rt = a.out.rate ? a.out.rate + ev : nullptr;
-    float* const o_op = a.out.over_power ? a.out.over_power + ev : nullptr;
+    const unsigned sIn = (unsigned)E * RIN, sOut = (unsigned)E * ROUT;
+    const size_t grp = blockIdx.x;  // records are tiled per warp (4 envs): each field is one 128 B line
+    const float* const in_b = PACKED ? a.in_rec + grp * (4 * RIN) + el * 8 + v : nullptr;
+    float* const out_b = PACKED ? a.out_rec + grp * (4 * ROUT) + el * 8 + v : nullptr;
+    const float* const ac_b = PACKED ? in_b : a.action + (size_t)e * 2 * V + vc;
+    const int* const ar_b = PACKED ? nullptr : ((FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr);
+    float* const o_ru = (!PACKED && a.out.reward_user) ? a.out.reward_user + ev : nullptr;
+    float* const o_buf = (!PACKED && a.out.DataBuf) ? a.out.DataBuf + ev : nullptr;
+    float* const o_dt = (!PACKED && a.out.data_t) ? a.out.data_t + ev : nullptr;
+    float* const o_dp = (!PACKED && a.out.data_p) ? a.out.data_p + ev : nullptr;
+    float* const o_rt = (!PACKED && a.out.rate) ? a.out.rate + ev : nullptr;
+    float* const o_op = (!PACKED && a.out.over_power) ? a.out.over_power + ev : nullptr;
     float* const o_rw = a.out.reward ? a.out.reward + e : nullptr;
     const unsigned Tm1 = (unsigned)(T - 1);
 
     auto load_in = [&](MarlIn& in, unsigned t) {
         const unsigned tc = min(t, Tm1);
-        const float* q = ac_b + (size_t)tc * s2V;
-        in.a0 = act ? __ldg(q) : 0.f;
-        in.a1 = act ? __ldg(q + V) : 0.f;
-        in.arr = (act && (FULL || ar_b != nullptr)) ? __ldg(ar_b + (size_t)tc * sV) : 0;
+        if constexpr (PACKED) {  // tile: a0[4][8] a1[4][8] arr[4][8]
+            const float* q = in_b + (size_t)tc * sIn;
+            in.a0 = __ldg(q);
+            in.a1 = __ldg(q + 32);
+            in.arr = __ldg(reinterpret_cast<const int*>(q) + 64);
+        } else {
+            const float* q = ac_b + (size_t)tc * s2V;
+            in.a0 = act ? __ldg(q) : 0.f;
+            in.a1 = act ? __ldg(q + V) : 0.f;
+            in.arr = (act && (FULL || ar_b != nullptr)) ? __ldg(ar_b + (size_t)tc * sV) : 0;
+        }
     };
 
     // state-independent part of a step
@@ -856,13 +905,18 @@ __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t
         const float glob = __fmul_rn(seg_sum<8>(act ? rew : 0.f), invV);               // MARL:721
         const float overp = fmaxf(0.f, __fsub_rn(__fadd_rn(h.P0, h.P1), Pmax));        // MARL:727-729
         if (act) {
-            const size_t o = (size_t)t * sV;
-            if (FULL || o_ru) o_ru[o] = rew;
-            if (FULL || o_buf) o_buf[o] = (float)buf;
-            if (FULL || o_dt) o_dt[o] = h.data_t;
-            if (FULL || o_dp) o_dp[o] = (float)local_done;
-            if (FULL || o_rt) o_rt[o] = h.rate;
-            if (!FULL && o_op) o_op[o] = overp;
+            if constexpr (PACKED) {  // tile: reward_user | DataBuf | data_t | data_p | rate, each [4][8]
+                float* q = out_b + (size_t)t * sOut;
+                q[0] = rew; q[32] = (float)buf; q[64] = h.data_t; q[96] = (float)local_done; q[128] = h.rate;
+            } else {
+                const size_t o = (size_t)t * sV;
+                if (FULL || o_ru) o_ru[o] = rew;
+                if (FULL || o_buf) o_buf[o] = (float)buf;
+                if (FULL || o_dt) o_dt[o] = h.data_t;
+                if (FULL || o_dp) o_dp[o] = (float)local_done;
+                if (FULL || o_rt) o_rt[o] = h.rate;
+                if (!FULL && o_op) o_op[o] = overp;
+            }
             if (v == 0 && (FULL || o_rw)) o_rw[(size_t)t * sE] = glob;
         }
         l_rate = h.rate; l_dt = h.data_t; l_dp = (float)local_done; l_rew = rew; l_glob = glob; l_overp = overp;

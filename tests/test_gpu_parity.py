@@ -206,3 +206,48 @@ def test_host_pipeline_multi_chunk_and_shard_stats():
     want = envs[0].stats.double().sum(dim=0).cpu().numpy()
     np.testing.assert_allclose(st[:16], want, rtol=1e-12, atol=1e-9)
     assert abs(st[16] - envs[0].reward.double().sum().item()) < 1e-6
+
+
+def test_packed_records_are_bit_identical_to_per_array_api():
+    """The packed record entry points (device and pinned-host pipelines) against the per-array
+    ones: same kernels' arithmetic, so every trace and the final state must match bit for bit."""
+    from ris_vec_marl_b200 import BatchedEnviron, RisvecError, encode_groups, marl_yaml_overrides
+
+    E, V, M, T = 1028, 8, 40, 37  # odd T; E % 4 == 0 as the tiled layout requires
+    gen = torch.Generator().manual_seed(21)
+    acts = torch.rand(T, E, 2, V, generator=gen)
+    ph = torch.rand(T, E, M, generator=gen) * 6.2831853
+    arr = torch.poisson(torch.full((T, E, V), 2.0), generator=gen).to(torch.int32)
+    for variant in ("sarl", "marl"):
+        over = marl_yaml_overrides() if variant == "marl" else {}
+        envs = [BatchedEnviron(variant, E, V, M, seed=5, **over) for _ in range(3)]
+        for e in envs:
+            e.make_new_game(); e.renew_positions(); e.compute_parms()
+            if variant == "marl":
+                e.optimize_phase_shift(); e.update_channel_gains()
+        if variant == "sarl":
+            ref = envs[0].rollout_sarl(acts.cuda(), ph.cuda(), arr.cuda())
+            rec = envs[1].pack_inputs(acts, arr, ph)
+            extra = {}
+        else:
+            part, ng = encode_groups([[0, 1], [3, 2], [4, 5], [6], [7]], V)
+            extra = dict(partner=torch.as_tensor(np.tile(part, (E, 1))), ngroups=torch.full((E,), ng, dtype=torch.int32))
+            names = ("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate")
+            ref = envs[0].rollout_marl(acts.cuda(), extra["partner"], extra["ngroups"], arr.cuda(), traces=names)
+            rec = envs[1].pack_inputs(acts, arr)
+        out_rec, rew = envs[1].rollout_packed(rec.cuda(), **extra)
+        got = envs[1].unpack_outputs(out_rec, rew)
+        h_out = torch.empty(out_rec.shape).pin_memory()
+        h_rew = torch.empty(rew.shape).pin_memory()
+        pinned = {k: v.pin_memory() for k, v in extra.items()}
+        envs[2].rollout_packed_host(rec.pin_memory(), h_out, h_rew, **pinned)
+        torch.cuda.synchronize()
+        got_h = envs[2].unpack_outputs(h_out, h_rew)
+        for k, v in ref.items():
+            assert torch.equal(v, got[k]), (variant, k)
+            assert torch.equal(v.cpu(), got_h[k]), (variant, "host", k)
+        for f in ("DataBuf", "vehicle_rate", "reward", "mec_queue_cycles", "step_ctr", "stats", "phase_real"):
+            assert torch.equal(envs[0].state(f), envs[1].state(f)) and torch.equal(envs[0].state(f), envs[2].state(f)), f
+    odd = BatchedEnviron("sarl", 6, 8, 40)  # E % 4 != 0: the tiled layout does not apply
+    with pytest.raises(RisvecError):
+        odd.rollout_packed(torch.zeros(2, 6 * (24 + 40)))

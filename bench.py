@@ -264,7 +264,7 @@ def main():
         trace_names = ("reward", "DataBuf", "data_t", "data_p", "over_power", "over_data", "rate")
     # SARL streams through the library's packed (tiled) records; MARL through the per-array entry
     # points, which measure faster for its 3-in / 6-out streams
-    packed = wl == "sarl"
+    packed = wl == "sarl" and V == 8 and M in (16, 40) and E % 4 == 0
     stats_sum = torch.zeros(17, dtype=torch.float64, device=dev)
     if packed:
         in_rec = env.pack_inputs(actions, arrivals, phases)
@@ -278,7 +278,10 @@ def main():
         out = env._alloc_traces(trace_names, T, trace_names)
 
         def one_step():
-            env.rollout_marl(actions, partner, ngroups, arrivals, out=out)
+            if wl == "marl":
+                env.rollout_marl(actions, partner, ngroups, arrivals, out=out)
+            else:
+                env.rollout_sarl(actions, phases, arrivals, out=out)
 
     pending = []
 
@@ -348,11 +351,16 @@ def main():
         h2d, d2h = h_in.numel() * 4, h_out.numel() * 4 + h_rew.numel() * 4
     else:
         h_act, h_arr = actions.cpu().pin_memory(), arrivals.cpu().pin_memory()
-        h_part, h_ng = partner.cpu().pin_memory(), ngroups.cpu().pin_memory()
         h_o = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in out.items()}
         h_rew = h_o["reward"]
-        run_host = lambda: env.rollout_marl_host(h_act, h_part, h_ng, h_arr, h_o)
-        h2d = (h_act.numel() + h_arr.numel() + h_part.numel() + h_ng.numel()) * 4
+        if wl == "marl":
+            h_part, h_ng = partner.cpu().pin_memory(), ngroups.cpu().pin_memory()
+            run_host = lambda: env.rollout_marl_host(h_act, h_part, h_ng, h_arr, h_o)
+            h2d = (h_act.numel() + h_arr.numel() + h_part.numel() + h_ng.numel()) * 4
+        else:
+            h_ph = phases.cpu().pin_memory()
+            run_host = lambda: env.rollout_sarl_host(h_act, h_ph, h_arr, h_o)
+            h2d = (h_act.numel() + h_arr.numel() + h_ph.numel()) * 4
         d2h = sum(v.numel() * 4 for v in h_o.values())
     run_host(); torch.cuda.synchronize()
     if world > 1:

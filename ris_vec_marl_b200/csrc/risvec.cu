@@ -124,7 +124,8 @@ template <int VP, int MPL, int WPE>
 int launch_sarl_cfg(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     constexpr int EPW = 32 / VP;
     const int blocks = (env->dims.E + EPW - 1) / EPW;
-    const size_t smem = ((size_t)EPW * (env->dims.M + 2) + (WPE > 1 ? WPE * 32 : 0)) * sizeof(float2);
+    const size_t MS = (size_t)((env->dims.M + 2 * WPE + 3) / 2) * 2;  // must match the kernel
+    const size_t smem = 6 * EPW * MS * sizeof(float) + (WPE > 1 ? 2 * WPE * 32 * sizeof(float2) : 0);
     auto kern = k_sarl_rollout<VP, MPL, WPE>;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, 32 * WPE, smem, st>>>(env->dims, env->st, env->params, a);

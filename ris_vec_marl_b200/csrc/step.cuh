@@ -252,183 +252,7 @@ __global__ void __launch_bounds__(128) k_marl_rollout(Dims d, State s, risvec_pa
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// SARL step (row a12): per step the V x M cascaded RIS reduction
-//   S_v = sum_m exp(j*phase_m) * phasor(v, m),  rate_v = ln(1 + P0_v * amp_v * |S_v|^2 / sigma^2)
-// The geometry phasor table (depends only on positions) is built once per launch in float64
-// and kept in registers: lane (env, v) of warp w holds elements [w*slice, (w+1)*slice).
-// WPE warps share one env group and combine their partial sums through shared memory.
-// ---------------------------------------------------------------------------------------
-__device__ __noinline__ void phasor_f32(double x, float* re, float* im) {
-    double s64, c64;
-    sincospi(x, &s64, &c64);
-    *re = (float)c64;
-    *im = (float)s64;
-}
-
-template <int VP, int MPL, int WPE>
-__global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
-    constexpr int EPW = 32 / VP;  // envs per warp (= per block)
-    extern __shared__ float2 sarl_smem[];
-    const int E = d.E, V = d.V, M = d.M;
-    const int MS = M + 2;  // padded env stride of the theta table (bank spread)
-    float2* th = sarl_smem;                // [EPW][MS]
-    float2* part = sarl_smem + EPW * MS;   // [WPE][32] (WPE > 1 only)
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int el = lane / VP, v = lane % VP;
-    const int e0 = blockIdx.x * EPW;
-    const int e = e0 + el;
-    const bool env_ok = e < E;
-    const bool act = env_ok && v < V;
-    const size_t ev = (size_t)e * V + v;
-    const int slice = (M + WPE - 1) / WPE;
-    const int m0 = w * slice;
-    const int m1 = min(M, m0 + slice);
-
-    // ---- geometry phasor table -> registers (float64 argument reduction, float32 storage)
-    float wr[MPL], wi[MPL];
-    {
-        const double delta = act ? d.angle_BR - s.angle[ev] : 0.0;
-#pragma unroll
-        for (int i = 0; i < MPL; ++i) {
-            const int m = m0 + i;
-            float re = 0.f, im = 0.f;
-            if (act && m < m1) phasor_f32((double)m * delta, &re, &im);
-            wr[i] = re;
-            wi[i] = im;
-        }
-    }
-    const bool cphase = (w == 0);
-    double buf = (act && cphase) ? s.databuf[ev] : 0.0;
-    const float coef = act ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
-    const long long step0 = env_ok ? s.step_ctr[e] : 0;
-
-    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
-    const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);       // SARL:331
-    const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));             // SARL:318-319
-    const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
-    const float invV = 1.0f / (float)V;
-    const float lam = (float)p.rate;
-    const int n_env_here = min(EPW, E - e0);
-
-    float o_rate = 0.f, o_dt = 0.f, o_dp = 0.f, o_overp = 0.f, o_overd = 0.f, o_rew = 0.f;
-    int o_arr = 0;
-
-    for (int t = 0; t < a.T; ++t) {
-        // (1) theta_m = exp(j*phase_m) for the block's envs (SARL:125-131); the EPW rows of
-        //     phase[t] are contiguous in HBM
-        const float* ph_t = a.phase + ((size_t)t * E + e0) * M;
-        const bool last = (t == a.T - 1);
-        for (int idx = threadIdx.x; idx < n_env_here * M; idx += 32 * WPE) {
-            const float ph = ph_t[idx];
-            float sn, cs;
-            sincosf(ph, &sn, &cs);
-            const int el2 = idx / M, m = idx - el2 * M;
-            th[el2 * MS + m] = make_float2(cs, sn);
-            if (last) s.phase_real[(size_t)e0 * M + idx] = ph;
-        }
-        if (WPE > 1) __syncthreads(); else __syncwarp();
-
-        // (2) cascaded reduction over this warp's element slice
-        float sr = 0.f, si = 0.f;
-        const float2* th_e = th + el * MS + m0;
-#pragma unroll
-        for (int i = 0; i < MPL; ++i) {
-            if (m0 + i < m1) {
-                const float2 tq = th_e[i];
-                sr = fmaf(tq.x, wr[i], sr);
-                sr = fmaf(-tq.y, wi[i], sr);
-                si = fmaf(tq.x, wi[i], si);
-                si = fmaf(tq.y, wr[i], si);
-            }
-        }
-        if (WPE > 1) {
-            part[w * 32 + lane] = make_float2(sr, si);
-            __syncthreads();
-            if (cphase) {
-                sr = 0.f; si = 0.f;
-#pragma unroll
-                for (int k = 0; k < WPE; ++k) {
-                    const float2 q = part[k * 32 + lane];
-                    sr += q.x; si += q.y;
-                }
-            }
-        } else {
-            __syncwarp();
-        }
-
-        // (3) per-vehicle queue update and reward (SARL:327-358), first warp of the block
-        if (cphase) {
-            const size_t tev = ((size_t)t * E + e) * V + v;
-            const size_t ta = ((size_t)t * E + e) * 2 * V + v;
-            const float a0 = act ? a.action[ta] : 0.f;
-            const float a1 = act ? a.action[ta + V] : 0.f;
-            int arr = 0;
-            if (act) arr = a.arrivals != nullptr ? a.arrivals[tev] : draw_arrival(d, e, v, step0 + t, lam);
-
-            const float g2 = sr * sr + si * si;
-            const float rate = log1pf(a0 * (coef * g2));  // natural log, SARL:159
-            const float data_t = rate * c_dt;
-            const float data_p = cbrtf(a1) * c_dp;
-            double nb = buf - ((double)data_t + (double)data_p);  // SARL:334
-            float overp = 0.f, overd = 0.f;
-            if (nb < 0.0) {  // SARL:336-339
-                const float b = (float)fmax(0.0, nb + (double)data_p) * c_rev;
-                overp = a1 - b * b * b;
-                overd = (float)(-nb);
-                nb = 0.0;
-            }
-            const float nbf = (float)nb;
-            const float base = -(t1 * (a0 + a1)) - (t2 * nbf);
-            const float ru = (nb > 0.0) ? base - pen1 : ((overd > 2.0f) ? base - pen2 : base);  // SARL:343-352
-            const float rew = seg_sum<VP>(act ? ru : 0.f) * invV;
-            buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, p.time_fast), 1000.0));  // SARL:354-356
-
-            if (act) {
-                if (a.out.DataBuf != nullptr) a.out.DataBuf[tev] = (float)buf;
-                if (a.out.data_t != nullptr) a.out.data_t[tev] = data_t;
-                if (a.out.data_p != nullptr) a.out.data_p[tev] = data_p;
-                if (a.out.over_power != nullptr) a.out.over_power[tev] = overp;
-                if (a.out.over_data != nullptr) a.out.over_data[tev] = overd;
-                if (a.out.rate != nullptr) a.out.rate[tev] = rate;
-                if (v == 0 && a.out.reward != nullptr) a.out.reward[(size_t)t * E + e] = rew;
-            }
-            o_rate = rate; o_dt = data_t; o_dp = data_p; o_overp = overp; o_overd = overd; o_rew = rew; o_arr = arr;
-        }
-    }
-
-    if (cphase && act && a.T > 0) {
-        s.databuf[ev] = buf;
-        s.rate[ev] = o_rate;
-        s.data_t[ev] = o_dt;
-        s.data_p[ev] = o_dp;
-        s.over_power[ev] = o_overp;
-        s.over_data[ev] = o_overd;
-        s.data_r[ev] = o_arr;
-        if (v == 0) {
-            s.reward[e] = o_rew;
-            s.step_ctr[e] = step0 + a.T;
-        }
-    }
-}
-
-// =========================================================================================
-// SARL fast path for V <= 8, M <= 8 * MPI (BASELINE configs 1-2: V = 8, M = 40, MPI = 5)
-// =========================================================================================
-// One warp = 4 envs; lane = (env el, part).  For the cascaded reduction the 8 lanes of an env
-// split the ELEMENT axis: lane `part` owns elements m = part + 8 i (i < MPI), evaluates
-// exp(j*phase_m) for them once, and multiplies them into the partial sums of ALL 8 vehicles.
-// The geometry phasors of its elements x 8 vehicles sit in registers as packed float2 pairs
-// (FFMA2 on Blackwell), stored in the lane-dependent vehicle order slot = v ^ part so that the
-// 3-stage reduce-scatter over lanes xor 4, 2, 1 needs no selects: a lane always keeps the low
-// half of its slots and sends the high half, and ends with the total S_v of vehicle v = part,
-// for which it then runs the per-vehicle queue update.
-// No shared memory, no block barrier.  Two consecutive steps are processed together: their
-// state-independent parts (phasors, reduction, rate, data_t, data_p) are independent
-// instruction streams -- the sin/cos evaluation is packed across the two steps (fp32x2) --
-// and only the DataBuf recursion is sequential.  Inputs of the next two steps are prefetched
-// into registers while the current ones compute.
-
+// ---- packed-fp32x2 math helpers shared by the SARL kernels
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 
 // sin/cos of two float32 angles (radians, |x| < ~1e4; RIS phases live in [0, 2*pi]) in packed
@@ -473,6 +297,239 @@ __device__ __forceinline__ float cbrt_sfu(float x) {
 __device__ __forceinline__ float2 shfl_xor2(float2 x, int o) {
     return make_float2(__shfl_xor_sync(kFull, x.x, o), __shfl_xor_sync(kFull, x.y, o));
 }
+
+// ---------------------------------------------------------------------------------------
+// SARL step (row a12): per step the V x M cascaded RIS reduction
+//   S_v = sum_m exp(j*phase_m) * phasor(v, m),  rate_v = ln(1 + P0_v * amp_v * |S_v|^2 / sigma^2)
+// The geometry phasor table (depends only on positions) is built once per launch in float64
+// and kept in registers: lane (env, v) of warp w holds elements [w*slice, (w+1)*slice).
+// WPE warps share one env group and combine their partial sums through shared memory.
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ void phasor_f32(double x, float* re, float* im) {
+    double s64, c64;
+    sincospi(x, &s64, &c64);
+    *re = (float)c64;
+    *im = (float)s64;
+}
+
+template <int VP, int MPL, int WPE>
+__global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
+    static_assert(MPL % 2 == 0, "elements are processed in FFMA2 pairs");
+    constexpr int EPW = 32 / VP;  // envs per warp (= per block)
+    constexpr int NT = 32 * WPE;
+    extern __shared__ float sarl_smem[];
+    const int E = d.E, V = d.V, M = d.M, T = a.T;
+    // theta = exp(j*phase) of the block's envs as three planes (cos, sin, -sin) so that two
+    // consecutive elements load as one float2 FFMA2 operand; double-buffered over steps.
+    // MS = padded plane stride (covers the odd-slice pad element, 8 B aligned pairs).
+    const int MS = ((M + 2 * WPE + 3) / 2) * 2;
+    const int plane = EPW * MS;
+    float* th = sarl_smem;                                              // [2][3][EPW][MS]
+    float2* part = reinterpret_cast<float2*>(sarl_smem + 6 * plane);    // [2][WPE][32] (WPE > 1)
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int el = lane / VP, v = lane % VP;
+    const int e0 = blockIdx.x * EPW;
+    const int e = e0 + el;
+    const bool env_ok = e < E;
+    const bool act = env_ok && v < V;
+    const size_t ev = (size_t)e * V + v;
+    const int slice = (((M + WPE - 1) / WPE) + 1) & ~1;  // even slices keep the float2 pairs aligned
+    const int m0 = w * slice;
+    const int m1 = min(M, m0 + slice);
+
+    // ---- geometry phasor table -> registers (float64 argument reduction), as element pairs
+    float2 WX[MPL / 2], WY[MPL / 2];
+    {
+        const double delta = act ? d.angle_BR - s.angle[ev] : 0.0;
+#pragma unroll
+        for (int i = 0; i < MPL; ++i) {
+            const int m = m0 + i;
+            float re = 0.f, im = 0.f;
+            if (act && m < m1) phasor_f32((double)m * delta, &re, &im);
+            if (i & 1) { WX[i >> 1].y = re; WY[i >> 1].y = im; }
+            else       { WX[i >> 1].x = re; WY[i >> 1].x = im; }
+        }
+    }
+    for (int i = threadIdx.x; i < 6 * plane; i += NT) th[i] = 0.f;  // pad elements must stay finite
+    const bool cphase = (w == 0);
+    double buf = (act && cphase) ? s.databuf[ev] : 0.0;
+    const float coef = act ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
+    const long long step0 = env_ok ? s.step_ctr[e] : 0;
+
+    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
+    const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);       // SARL:331
+    const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));             // SARL:318-319
+    const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
+    const float invV = 1.0f / (float)V;
+    const float lam = (float)p.rate;
+    const int n_env_here = min(EPW, E - e0);
+    const int n_ph = n_env_here * M;  // the EPW rows of phase[t] are contiguous in HBM
+
+    float o_rate = 0.f, o_dt = 0.f, o_dp = 0.f, o_overp = 0.f, o_overd = 0.f, o_rew = 0.f;
+    int o_arr = 0;
+
+    // theta(t) -> smem buffer t & 1: thread k handles elements k, k + NT, ... in packed pairs.
+    // The first pair of every step is prefetched one step ahead into (pf0, pf1).
+    float pf0 = 0.f, pf1 = 0.f;
+    auto fetch_phase = [&](int t) {
+        if (t < T) {
+            const float* ph_t = a.phase + ((size_t)t * E + e0) * M;
+            pf0 = (int)threadIdx.x < n_ph ? __ldg(ph_t + threadIdx.x) : 0.f;
+            pf1 = (int)threadIdx.x + NT < n_ph ? __ldg(ph_t + threadIdx.x + NT) : 0.f;
+        }
+    };
+    auto produce_theta = [&](int t) {
+        const float* ph_t = a.phase + ((size_t)t * E + e0) * M;
+        float* c_pl = th + (t & 1) * 3 * plane;
+        float* s_pl = c_pl + plane;
+        float* n_pl = s_pl + plane;
+        for (int idx = threadIdx.x; idx < n_ph; idx += 2 * NT) {
+            const int idx2 = idx + NT;
+            const bool first = idx == (int)threadIdx.x;
+            const float ph0 = first ? pf0 : __ldg(ph_t + idx);
+            const float ph1 = first ? pf1 : (idx2 < n_ph ? __ldg(ph_t + idx2) : 0.f);
+            float2 sn, cs;
+            sincos_fast2(make_float2(ph0, ph1), &sn, &cs);  // SARL:125-131
+            const int ea = idx / M, ma = idx - ea * M;
+            c_pl[ea * MS + ma] = cs.x; s_pl[ea * MS + ma] = sn.x; n_pl[ea * MS + ma] = -sn.x;
+            if (idx2 < n_ph) {
+                const int eb = idx2 / M, mb = idx2 - eb * M;
+                c_pl[eb * MS + mb] = cs.y; s_pl[eb * MS + mb] = sn.y; n_pl[eb * MS + mb] = -sn.y;
+            }
+            if (t == T - 1) {
+                s.phase_real[(size_t)e0 * M + idx] = ph0;
+                if (idx2 < n_ph) s.phase_real[(size_t)e0 * M + idx2] = ph1;
+            }
+        }
+    };
+    // scalar inputs of the C-phase warp, prefetched one step ahead
+    float na0 = 0.f, na1 = 0.f;
+    int narr = 0;
+    auto fetch_scalars = [&](int t) {
+        if (cphase && act && t < T) {
+            const size_t ta = ((size_t)t * E + e) * 2 * V + v;
+            na0 = __ldg(a.action + ta);
+            na1 = __ldg(a.action + ta + V);
+            narr = a.arrivals != nullptr ? __ldg(a.arrivals + ((size_t)t * E + e) * V + v) : 0;
+        }
+    };
+
+    __syncthreads();  // zero fill done
+    fetch_phase(0);
+    fetch_scalars(0);
+    if (T > 0) produce_theta(0);
+    fetch_phase(1);
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) produce_theta(t + 1);  // overlaps with this step's MACs (other buffer)
+        fetch_phase(t + 2);
+        const float a0 = na0, a1 = na1;
+        const int arr_in = narr;
+        fetch_scalars(t + 1);
+
+        // (2) cascaded reduction over this warp's element slice, two elements per FFMA2
+        const float* c_pl = th + (t & 1) * 3 * plane + el * MS + m0;
+        const float2* c2 = reinterpret_cast<const float2*>(c_pl);
+        const float2* s2 = reinterpret_cast<const float2*>(c_pl + plane);
+        const float2* n2 = reinterpret_cast<const float2*>(c_pl + 2 * plane);
+        float2 REa = make_float2(0.f, 0.f), IMa = REa, REb = REa, IMb = REa;
+#pragma unroll
+        for (int i = 0; i < MPL / 2; i += 2) {
+            if (m0 + 2 * i < m1) {
+                const float2 tx = c2[i], ty = s2[i], nty = n2[i];
+                REa = __ffma2_rn(tx, WX[i], REa); REa = __ffma2_rn(nty, WY[i], REa);
+                IMa = __ffma2_rn(tx, WY[i], IMa); IMa = __ffma2_rn(ty, WX[i], IMa);
+            }
+            if (i + 1 < MPL / 2 && m0 + 2 * (i + 1) < m1) {
+                const float2 tx = c2[i + 1], ty = s2[i + 1], nty = n2[i + 1];
+                REb = __ffma2_rn(tx, WX[i + 1], REb); REb = __ffma2_rn(nty, WY[i + 1], REb);
+                IMb = __ffma2_rn(tx, WY[i + 1], IMb); IMb = __ffma2_rn(ty, WX[i + 1], IMb);
+            }
+        }
+        float sr = (REa.x + REa.y) + (REb.x + REb.y);
+        float si = (IMa.x + IMa.y) + (IMb.x + IMb.y);
+        if (WPE > 1) {
+            float2* pt = part + (t & 1) * WPE * 32;
+            pt[w * 32 + lane] = make_float2(sr, si);
+            __syncthreads();  // also publishes theta(t + 1)
+            if (cphase) {
+                sr = 0.f; si = 0.f;
+#pragma unroll
+                for (int k = 0; k < WPE; ++k) {
+                    const float2 q = pt[k * 32 + lane];
+                    sr += q.x; si += q.y;
+                }
+            }
+        } else {
+            __syncwarp();
+        }
+
+        // (3) per-vehicle queue update and reward (SARL:327-358), first warp of the block
+        if (cphase) {
+            const size_t tev = ((size_t)t * E + e) * V + v;
+            int arr = arr_in;
+            if (act && a.arrivals == nullptr) arr = draw_arrival(d, e, v, step0 + t, lam);
+
+            const float g2 = __fmaf_rn(sr, sr, __fmul_rn(si, si));
+            const float rate = log1p_sfu(__fmul_rn(a0, __fmul_rn(coef, g2)));  // natural log, SARL:159
+            const float data_t = __fmul_rn(rate, c_dt);
+            const float data_p = __fmul_rn(cbrt_sfu(a1), c_dp);
+            const double raw = __dsub_rn(buf, __dadd_rn((double)data_t, (double)data_p));  // SARL:334
+            const bool neg = raw < 0.0;
+            const float b = __fmul_rn((float)fmax(0.0, raw + (double)data_p), c_rev);
+            const float overp = neg ? __fsub_rn(a1, __fmul_rn(__fmul_rn(b, b), b)) : 0.f;  // SARL:336-339
+            const float overd = neg ? (float)(-raw) : 0.f;
+            const double nb = neg ? 0.0 : raw;
+            const float base = __fsub_rn(-__fmul_rn(t1, __fadd_rn(a0, a1)), __fmul_rn(t2, (float)nb));
+            const float pen = (nb > 0.0) ? pen1 : ((overd > 2.0f) ? pen2 : 0.f);  // SARL:343-352
+            const float rew = __fmul_rn(seg_sum<VP>(act ? __fsub_rn(base, pen) : 0.f), invV);
+            buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, p.time_fast), 1000.0));  // SARL:354-356
+
+            if (act) {
+                if (a.out.DataBuf != nullptr) a.out.DataBuf[tev] = (float)buf;
+                if (a.out.data_t != nullptr) a.out.data_t[tev] = data_t;
+                if (a.out.data_p != nullptr) a.out.data_p[tev] = data_p;
+                if (a.out.over_power != nullptr) a.out.over_power[tev] = overp;
+                if (a.out.over_data != nullptr) a.out.over_data[tev] = overd;
+                if (a.out.rate != nullptr) a.out.rate[tev] = rate;
+                if (v == 0 && a.out.reward != nullptr) a.out.reward[(size_t)t * E + e] = rew;
+            }
+            o_rate = rate; o_dt = data_t; o_dp = data_p; o_overp = overp; o_overd = overd; o_rew = rew; o_arr = arr;
+        }
+        if (WPE == 1) __syncwarp();  // theta(t + 1) of this warp is complete before the next MACs
+    }
+
+    if (cphase && act && T > 0) {
+        s.databuf[ev] = buf;
+        s.rate[ev] = o_rate;
+        s.data_t[ev] = o_dt;
+        s.data_p[ev] = o_dp;
+        s.over_power[ev] = o_overp;
+        s.over_data[ev] = o_overd;
+        s.data_r[ev] = o_arr;
+        if (v == 0) {
+            s.reward[e] = o_rew;
+            s.step_ctr[e] = step0 + T;
+        }
+    }
+}
+
+// =========================================================================================
+// SARL fast path for V <= 8, M <= 8 * MPI (BASELINE configs 1-2: V = 8, M = 40, MPI = 5)
+// =========================================================================================
+// One warp = 4 envs; lane = (env el, part).  For the cascaded reduction the 8 lanes of an env
+// split the ELEMENT axis: lane `part` owns elements m = part + 8 i (i < MPI), evaluates
+// exp(j*phase_m) for them once, and multiplies them into the partial sums of ALL 8 vehicles.
+// The geometry phasors of its elements x 8 vehicles sit in registers as packed float2 pairs
+// (FFMA2 on Blackwell), stored in the lane-dependent vehicle order slot = v ^ part so that the
+// 3-stage reduce-scatter over lanes xor 4, 2, 1 needs no selects: a lane always keeps the low
+// half of its slots and sends the high half, and ends with the total S_v of vehicle v = part,
+// for which it then runs the per-vehicle queue update.
+// No shared memory, no block barrier.  Two consecutive steps are processed together: their
+// state-independent parts (phasors, reduction, rate, data_t, data_p) are independent
+// instruction streams -- the sin/cos evaluation is packed across the two steps (fp32x2) --
+// and only the DataBuf recursion is sequential.  Inputs of the next two steps are prefetched
+// into registers while the current ones compute.
 
 // theta_m * w[slot] accumulated for the 4 slot pairs of one element
 __device__ __forceinline__ void sarl_mac(float cs, float sn, const float2 (&WX)[4], const float2 (&WY)[4],

@@ -85,7 +85,8 @@ class BatchedEnviron:
             check(self._lib.risvec_field(self._h, i, C.byref(ptr), C.byref(rows), C.byref(cols), C.byref(eb),
                                          C.byref(fl)))
             typestr = ("<f" if fl.value else "<i") + str(eb.value)
-            shape = (rows.value, cols.value) if cols.value > 1 else (rows.value,)
+            per_env_scalar = name in ("reward", "mec_queue_cycles", "step_ctr")
+            shape = (rows.value,) if per_env_scalar else (rows.value, cols.value)
             self._views[name] = torch.as_tensor(_DevView(ptr.value, shape, typestr), device=self.device)
         self._views["last_power_W"] = self._views["last_power_W"].view(self.E, 2, self.V)
 

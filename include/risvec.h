@@ -232,6 +232,15 @@ int risvec_rollout_marl_host(risvec_env_t* env, int T, const float* action, cons
 int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, const float* phase,
                              const int32_t* arrivals, const risvec_sarl_out_t* out, void* stream);
 
+/* Driver-side glue on device.
+ * risvec_observe: marl_get_state (marl_train_bcd.py:819-827) / get_state (ddpg_train.py:47-73) for
+ * every agent of every env: obs [E, V, n_theta + 5] f32 where n_theta = 0 (MARL) or M / V (SARL).
+ * risvec_map_actions: raw policy outputs in [-1,1] -> env actions.  MARL (marl_train_bcd.py:1601-1608):
+ * raw [E,V,2] -> action [E,2,V] (phase ignored).  SARL (ddpg_train.py:151-160): raw [E, 2V+M] ->
+ * action [E,2,V] and phase [E,M] radians. */
+int risvec_observe(risvec_env_t* env, float* obs, void* stream);
+int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float* phase, void* stream);
+
 /* Episode statistics for the multi-GPU reduction: sums over this shard's E envs of the
  * RISVEC_F_STATS columns and of RISVEC_F_REWARD, written to out [RISVEC_NSTAT + 1] f64 (device). */
 int risvec_shard_stats(risvec_env_t* env, double* out, void* stream);

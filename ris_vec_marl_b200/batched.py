@@ -326,6 +326,29 @@ class BatchedEnviron:
                                                             self._hp(ngroups), self._hp(out_rec), self._hp(reward),
                                                             self.stream))
 
+    # ---- driver-side glue on device
+    def observe(self, out=None):
+        """Per-agent observations [E, V, W]: MARL W = 5 (marl_train_bcd.py:819-827), SARL
+        W = M // V + 5 with the agent's RIS phase slice first (ddpg_train.py:47-73)."""
+        W = (self.M // self.V if self.variant == "sarl" else 0) + 5
+        if out is None:
+            out = torch.empty(self.E, self.V, W, dtype=torch.float32, device=self.device)
+        check(self._lib.risvec_observe(self._h, self._p(out), self.stream))
+        return out
+
+    def map_actions(self, raw):
+        """Raw policy outputs in [-1, 1] -> env actions.  MARL: raw [E,V,2] -> action [E,2,V]
+        (marl_train_bcd.py:1601-1608); SARL: raw [E,2V+M] -> (action [E,2,V], phase [E,M])
+        (ddpg_train.py:151-160)."""
+        r = self._dev(raw, torch.float32)
+        act = torch.empty(self.E, 2, self.V, dtype=torch.float32, device=self.device)
+        if self.variant == "marl":
+            check(self._lib.risvec_map_actions(self._h, self._p(r), self._p(act), self._p(None), self.stream))
+            return act
+        ph = torch.empty(self.E, self.M, dtype=torch.float32, device=self.device)
+        check(self._lib.risvec_map_actions(self._h, self._p(r), self._p(act), self._p(ph), self.stream))
+        return act, ph
+
     # ------------------------------------------------------------------ stats / checkpoint
     def last_stats(self):
         """{name: tensor [E]} of the reference's `last_*` attributes after the latest step."""

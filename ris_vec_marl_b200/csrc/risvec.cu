@@ -784,6 +784,30 @@ int risvec_rollout_marl_packed_host(risvec_env_t* env, int T, const void* in_rec
                                 });
 }
 
+int risvec_observe(risvec_env_t* env, float* obs, void* stream) {
+    if (!env || !obs) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const int n_theta = env->dims.variant == RISVEC_VARIANT_SARL ? env->dims.M / env->dims.V : 0;
+    const long long n = (long long)env->dims.E * env->dims.V;
+    k_observe<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, obs, n_theta);
+    return check_launch(env, "k_observe");
+}
+
+int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float* phase, void* stream) {
+    if (!env || !raw || !action) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const Dims& d = env->dims;
+    if (d.variant == RISVEC_VARIANT_MARL) {
+        const long long n = (long long)d.E * d.V;
+        k_map_actions_marl<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, env->params, raw, action);
+        return check_launch(env, "k_map_actions_marl");
+    }
+    if (!phase) return fail(RISVEC_ERR_INVALID, "SARL action mapping needs the phase output");
+    const long long n = (long long)d.E * (2 * d.V + d.M);
+    k_map_actions_sarl<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, raw, action, phase);
+    return check_launch(env, "k_map_actions_sarl");
+}
+
 int risvec_shard_stats(risvec_env_t* env, double* out, void* stream) {
     if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(env->device));

@@ -1047,4 +1047,50 @@ __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t
     }
 }
 
+// =========================================================================================
+// Driver-side glue on device: observation assembly and action mapping
+// =========================================================================================
+// marl_get_state (marl_train_bcd.py:819-827): per agent [DataBuf/10, data_t/10, data_p/10,
+// over_data/10, vehicle_rate/20]; get_state (ddpg_train.py:47-73) prepends the agent's slice of
+// `elements_phase_shift_real` (theta_number = int(M / n_veh) raw radians).  obs is [E, V, W].
+__global__ void k_observe(Dims d, State s, float* __restrict__ obs, int n_theta) {
+    const size_t ix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= (size_t)d.E * d.V) return;
+    const int e = (int)(ix / d.V), v = (int)(ix % d.V);
+    const int W = n_theta + 5;
+    float* o = obs + ix * W;
+    for (int k = 0; k < n_theta; ++k) o[k] = s.phase_real[(size_t)e * d.M + v * n_theta + k];
+    o[n_theta + 0] = (float)(s.databuf[ix] / 10.0);
+    o[n_theta + 1] = s.data_t[ix] / 10.f;
+    o[n_theta + 2] = s.data_p[ix] / 10.f;
+    o[n_theta + 3] = s.over_data[ix] / 10.f;
+    o[n_theta + 4] = s.rate[ix] / 20.f;
+}
+
+// MARL action mapping (marl_train_bcd.py:1601-1608): raw [E,V,2] in [-1,1] (per-agent tanh power
+// heads) -> action_for_env [E,2,V]: clip to +-0.999, (a + 1) / 2, CPU share floored.
+__global__ void k_map_actions_marl(Dims d, risvec_params_t p, const float* __restrict__ raw, float* __restrict__ act) {
+    const size_t ix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= (size_t)d.E * d.V) return;
+    const int e = (int)(ix / d.V), v = (int)(ix % d.V);
+    const float floor_f = (float)fmax(0.0, fmin(p.cpu_share_floor, 0.95));
+    const float a0 = (fminf(fmaxf(raw[ix * 2 + 0], -0.999f), 0.999f) + 1.f) / 2.f;
+    const float a1 = (fminf(fmaxf(raw[ix * 2 + 1], -0.999f), 0.999f) + 1.f) / 2.f;
+    act[((size_t)e * 2 + 0) * d.V + v] = a0;
+    act[((size_t)e * 2 + 1) * d.V + v] = fmaxf(a1, floor_f);
+}
+
+// SARL action mapping (ddpg_train.py:151-160): raw [E, 2V + M] in [-1,1] -> power [E,2,V] =
+// (a + 1) / 2 and phase [E,M] = (a + 1) / 2 * 2 pi.
+__global__ void k_map_actions_sarl(Dims d, const float* __restrict__ raw, float* __restrict__ act,
+                                   float* __restrict__ phase) {
+    const int W = 2 * d.V + d.M;
+    const size_t ix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= (size_t)d.E * W) return;
+    const int e = (int)(ix / W), k = (int)(ix % W);
+    const float a = (fminf(fmaxf(raw[ix], -0.999f), 0.999f) + 1.f) / 2.f;
+    if (k < 2 * d.V) act[(size_t)e * 2 * d.V + k] = a;
+    else phase[(size_t)e * d.M + (k - 2 * d.V)] = a * 3.14159265358979323846f * 2.f;
+}
+
 }  // namespace risvec

@@ -251,3 +251,42 @@ def test_packed_records_are_bit_identical_to_per_array_api():
     odd = BatchedEnviron("sarl", 6, 8, 40)  # E % 4 != 0: the tiled layout does not apply
     with pytest.raises(RisvecError):
         odd.rollout_packed(torch.zeros(2, 6 * (24 + 40)))
+
+
+def test_observation_and_action_mapping_match_the_driver_formulas():
+    """Device glue vs a numpy restatement of the drivers' own functions
+    (marl_train_bcd.py:819-827,1601-1608; ddpg_train.py:47-73,151-160)."""
+    from ris_vec_marl_b200 import BatchedEnviron, marl_yaml_overrides
+
+    E, V, M = 33, 8, 40
+    rng = np.random.default_rng(5)
+    # MARL
+    env = BatchedEnviron("marl", E, V, M, **marl_yaml_overrides())
+    env.make_new_game(); env.renew_positions(); env.compute_parms(); env.optimize_phase_shift(); env.update_channel_gains()
+    raw = (rng.random((E, V, 2)) * 2.2 - 1.1).astype(np.float32)
+    act = env.map_actions(raw).cpu().numpy()
+    c = np.clip(raw, -0.999, 0.999)
+    want = np.stack([(c[..., 0] + 1) / 2, np.maximum((c[..., 1] + 1) / 2, 0.10)], axis=1)
+    np.testing.assert_allclose(act, want, rtol=1e-6, atol=1e-7)
+    part = np.full((E, V), -1, dtype=np.int32)
+    env.step_marl(act, part, np.full(E, V, dtype=np.int32))
+    obs = env.observe().cpu().numpy()
+    f = lambda n: env.state(n).cpu().numpy().astype(np.float64)
+    want = np.stack([f("DataBuf") / 10, f("data_t") / 10, f("data_p") / 10, f("over_data") / 10, f("vehicle_rate") / 20], -1)
+    np.testing.assert_allclose(obs, want, rtol=1e-6, atol=1e-7)
+    # SARL
+    env = BatchedEnviron("sarl", E, V, M)
+    env.make_new_game(); env.renew_positions(); env.compute_parms()
+    raw = (rng.random((E, 2 * V + M)) * 2.2 - 1.1).astype(np.float32)
+    act, ph = (t.cpu().numpy() for t in env.map_actions(raw))
+    c = (np.clip(raw, -0.999, 0.999) + 1) / 2
+    np.testing.assert_allclose(act, c[:, :2 * V].reshape(E, 2, V), rtol=1e-6)
+    np.testing.assert_allclose(ph, c[:, 2 * V:] * np.pi * 2, rtol=1e-6)
+    env.step_sarl(act, ph)
+    obs = env.observe().cpu().numpy()
+    f = lambda n: env.state(n).cpu().numpy().astype(np.float64)
+    th = f("phase_real").reshape(E, V, M // V)
+    want = np.concatenate([th, np.stack([f("DataBuf") / 10, f("data_t") / 10, f("data_p") / 10, f("over_data") / 10,
+                                         f("vehicle_rate") / 20], -1)], axis=-1)
+    np.testing.assert_allclose(obs, want, rtol=1e-6, atol=1e-7)
+    assert obs.reshape(E, -1).shape[1] == 80  # the DDPG input size of ddpg_train.py:75

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Actor-in-the-loop rollout (BASELINE config 5 shape, one GPU's share): per step
+observe -> V per-agent policy MLPs in torch (5 -> 512 -> LN -> 256 -> LN -> 2, tanh; the power head
+of Simulation-MARL-BCD/sac_agent.py:23-34) -> map_actions -> Environ.step (T = 1 launch).
+Random-init weights, no learner update.  Reports env-steps/s eager and replayed as a CUDA graph
+(the launch-bound regime the fused T-step rollout of bench.py avoids)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from ris_vec_marl_b200 import BatchedEnviron, encode_groups, marl_yaml_overrides  # noqa: E402
+
+
+class Actors(torch.nn.Module):
+    """V independent policy networks evaluated as batched matmuls ([V, E, .] x [V, ., .])."""
+
+    def __init__(self, V, dev):
+        super().__init__()
+        g = torch.Generator(device="cpu").manual_seed(0)
+        mk = lambda i, o: torch.nn.Parameter((torch.randn(V, i, o, generator=g) / i ** 0.5).to(dev))
+        self.w1, self.w2, self.w3 = mk(5, 512), mk(512, 256), mk(256, 2)
+        self.b1 = torch.nn.Parameter(torch.zeros(V, 1, 512, device=dev))
+        self.b2 = torch.nn.Parameter(torch.zeros(V, 1, 256, device=dev))
+        self.b3 = torch.nn.Parameter(torch.zeros(V, 1, 2, device=dev))
+
+    @torch.no_grad()
+    def forward(self, obs):  # obs [E, V, 5] -> raw actions [E, V, 2] in (-1, 1)
+        x = obs.transpose(0, 1)
+        x = torch.relu(torch.nn.functional.layer_norm(torch.baddbmm(self.b1, x, self.w1), (512,)))
+        x = torch.relu(torch.nn.functional.layer_norm(torch.baddbmm(self.b2, x, self.w2), (256,)))
+        return torch.tanh(torch.baddbmm(self.b3, x, self.w3)).transpose(0, 1).contiguous()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=8192)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--actor-dtype", default="fp32", choices=["fp32", "tf32", "bf16"])
+    a = ap.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = a.actor_dtype == "tf32"
+    dev = torch.device("cuda", 0)
+    E, V, M = a.envs, 8, 40
+    env = BatchedEnviron("marl", E, V, M, **marl_yaml_overrides())
+    env.make_new_game(); env.renew_positions(); env.compute_parms(); env.optimize_phase_shift(); env.update_channel_gains()
+    part, ng = encode_groups([[0, 1], [2, 3], [4, 5], [6], [7]], V)
+    partner = torch.as_tensor(np.tile(part, (E, 1))).to(dev)
+    ngroups = torch.full((E,), ng, dtype=torch.int32, device=dev)
+    actors = Actors(V, dev)
+    if a.actor_dtype == "bf16":
+        actors = actors.to(torch.bfloat16)
+    obs = torch.empty(E, V, 5, device=dev)
+
+    def step():
+        env.observe(out=obs)
+        x = obs.to(torch.bfloat16) if a.actor_dtype == "bf16" else obs
+        act = env.map_actions(actors(x).float())
+        env.step_marl(act, partner, ngroups)  # arrivals: on-device Philox
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) * 1e-3
+
+    for _ in range(5):
+        step()
+    res = {"config": {"envs": E, "V": V, "M": M, "steps": a.steps, "actor": "8 x MLP 5-512-256-2 (bmm), " + a.actor_dtype}}
+    sec = timed(step, a.steps)
+    res["eager_env_steps_per_s"] = E * a.steps / sec
+    res["eager_us_per_step"] = sec / a.steps * 1e6
+    try:
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            step()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=s):
+                step()
+        sec = timed(g.replay, a.steps)
+        res["graph_env_steps_per_s"] = E * a.steps / sec
+        res["graph_us_per_step"] = sec / a.steps * 1e6
+    except Exception as exc:  # capture is best-effort
+        res["graph_error"] = repr(exc)[:200]
+    res["mean_reward"] = float(env.reward.mean())
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -312,6 +312,27 @@ __device__ __noinline__ void phasor_f32(double x, float* re, float* im) {
     *im = (float)s64;
 }
 
+// float64 complex helpers for building phasor tables: exp(j*pi*m*delta) = z^m with
+// z = exp(j*pi*delta) evaluated ONCE per vehicle (sincospi) and raised by float64 complex
+// multiplications (each ~1e-16 relative), instead of one sincospi per table entry.
+__device__ __noinline__ double2 unit_phasor64(double delta) {
+    double s64, c64;
+    sincospi(delta, &s64, &c64);
+    return make_double2(c64, s64);
+}
+__device__ __forceinline__ double2 cmul64(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cpow64(double2 z, unsigned n) {  // z^n by squaring
+    double2 r = make_double2(1.0, 0.0);
+    while (n) {
+        if (n & 1u) r = cmul64(r, z);
+        z = cmul64(z, z);
+        n >>= 1;
+    }
+    return r;
+}
+
 template <int VP, int MPL, int WPE>
 __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
     static_assert(MPL % 2 == 0, "elements are processed in FFMA2 pairs");
@@ -340,14 +361,16 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
     // ---- geometry phasor table -> registers (float64 argument reduction), as element pairs
     float2 WX[MPL / 2], WY[MPL / 2];
     {
-        const double delta = act ? d.angle_BR - s.angle[ev] : 0.0;
+        // w(v, m0 + i) = z^m0 * z^i in float64 from one sincospi per lane
+        const double2 z = unit_phasor64(act ? d.angle_BR - s.angle[ev] : 0.0);
+        double2 wv = cpow64(z, (unsigned)m0);
 #pragma unroll
         for (int i = 0; i < MPL; ++i) {
-            const int m = m0 + i;
-            float re = 0.f, im = 0.f;
-            if (act && m < m1) phasor_f32((double)m * delta, &re, &im);
+            const bool on = act && (m0 + i < m1);
+            const float re = on ? (float)wv.x : 0.f, im = on ? (float)wv.y : 0.f;
             if (i & 1) { WX[i >> 1].y = re; WY[i >> 1].y = im; }
             else       { WX[i >> 1].x = re; WY[i >> 1].x = im; }
+            wv = cmul64(wv, z);
         }
     }
     for (int i = threadIdx.x; i < 6 * plane; i += NT) th[i] = 0.f;  // pad elements must stay finite
@@ -579,19 +602,24 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
     // ---- geometry phasors of my elements for the 8 vehicles (slot = v ^ part) -> registers
     float2 WX[MPI][4], WY[MPI][4];
     {
-        const double my_delta = d.angle_BR - s.angle[ev];
+        // one sincospi per lane: z of my own vehicle; the other vehicles' z arrive by shuffle and
+        // w(v2, part + 8 i) = z^part * (z^8)^i is formed in float64, rounded to float32 once
+        const double2 my_z = unit_phasor64(d.angle_BR - s.angle[ev]);
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl) {
             const int v2 = sl ^ part;
-            const double dv = __shfl_sync(kFull, my_delta, (lane & ~7) + v2);
+            const int src = (lane & ~7) + v2;
+            const double2 z = make_double2(__shfl_sync(kFull, my_z.x, src), __shfl_sync(kFull, my_z.y, src));
             const bool ok2 = env_ok && v2 < V;
+            double2 w = cpow64(z, (unsigned)part);
+            const double2 z2 = cmul64(z, z), z4 = cmul64(z2, z2), z8 = cmul64(z4, z4);
 #pragma unroll
             for (int i = 0; i < MPI; ++i) {
-                const int m = part + 8 * i;
-                float re = 0.f, im = 0.f;
-                if (ok2 && m < M) phasor_f32((double)m * dv, &re, &im);
+                const bool on = ok2 && (part + 8 * i < M);
+                const float re = on ? (float)w.x : 0.f, im = on ? (float)w.y : 0.f;
                 if (sl & 1) { WX[i][sl >> 1].y = re; WY[i][sl >> 1].y = im; }
                 else        { WX[i][sl >> 1].x = re; WY[i][sl >> 1].x = im; }
+                w = cmul64(w, z8);
             }
         }
     }

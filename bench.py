@@ -289,11 +289,11 @@ def main():
         # the only collective on the path: NCCL sum of a 17-entry f64 vector.  It is
         # issued asynchronously (NCCL's own stream) so the next rollout overlaps it; `drain_stats`
         # waits for all of them inside the timed region.
-        sv = env.shard_stats()
         if world > 1:
+            sv = env.shard_stats()
             pending.append((dist.all_reduce(sv, async_op=True), sv))
         else:
-            stats_sum.add_(sv)
+            env.shard_stats(out=stats_sum, accumulate=True)
 
     def drain_stats():
         for work, sv in pending:

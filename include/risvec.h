@@ -242,8 +242,9 @@ int risvec_observe(risvec_env_t* env, float* obs, void* stream);
 int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float* phase, void* stream);
 
 /* Episode statistics for the multi-GPU reduction: sums over this shard's E envs of the
- * RISVEC_F_STATS columns and of RISVEC_F_REWARD, written to out [RISVEC_NSTAT + 1] f64 (device). */
-int risvec_shard_stats(risvec_env_t* env, double* out, void* stream);
+ * RISVEC_F_STATS columns and of RISVEC_F_REWARD, written (accumulate = 0) or added (accumulate != 0)
+ * to out [RISVEC_NSTAT + 1] f64 (device). */
+int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream);
 
 /* number of kernels this handle has launched so far (bench.py reports it as gpu_launches) */
 int64_t risvec_launch_count(const risvec_env_t* env);

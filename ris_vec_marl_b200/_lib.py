@@ -120,7 +120,7 @@ EXPORTS = {
                                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_map_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "risvec_shard_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "risvec_shard_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "risvec_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

@@ -355,10 +355,13 @@ class BatchedEnviron:
         st = self._views["stats"]
         return {n: st[:, i] for i, n in enumerate(STAT_COLUMNS)}
 
-    def shard_stats(self):
-        """f64 [NSTAT + 1] sums over this shard's envs (stats columns, then global reward)."""
-        out = torch.empty(NSTAT + 1, dtype=torch.float64, device=self.device)
-        check(self._lib.risvec_shard_stats(self._h, self._p(out), self.stream))
+    def shard_stats(self, out=None, accumulate=False):
+        """f64 [NSTAT + 1] sums over this shard's envs (stats columns, then global reward);
+        with `out` given the sums are written into it (or added, `accumulate=True`)."""
+        if out is None:
+            out = torch.empty(NSTAT + 1, dtype=torch.float64, device=self.device)
+            accumulate = False
+        check(self._lib.risvec_shard_stats(self._h, self._p(out), 1 if accumulate else 0, self.stream))
         return out
 
     def state_dict(self):

@@ -177,30 +177,28 @@ struct Carver {
     }
 };
 
-__global__ void k_shard_stats(Dims d, State s, double* out) {
-    // each block sums a contiguous slab of envs for all columns (coalesced 64 B rows), then adds
-    // its 17 partial sums to `out` (zeroed by the caller) with float64 atomics
-    __shared__ double red[8][RISVEC_NSTAT + 1];
-    const int col = threadIdx.x & 15, row = threadIdx.x >> 4;  // 16 columns x 16 env rows per pass
-    const int per_block = (d.E + gridDim.x - 1) / gridDim.x;
-    const int e0 = blockIdx.x * per_block, e1 = min(d.E, e0 + per_block);
+__global__ void __launch_bounds__(1024) k_shard_stats(Dims d, State s, double* out) {
+    // block b sums the envs b*64 + row, + 64*gridDim.x, ... : thread (row, col) reads stats column
+    // col (coalesced 64 B rows), float64 partial sums, shared-memory tree over the 64 rows, then
+    // 17 float64 atomics per block into `out` (zeroed by the caller unless it accumulates)
+    __shared__ double red[64][RISVEC_NSTAT + 1];
+    const int col = threadIdx.x & 15, row = threadIdx.x >> 4;
     double acc = 0.0, racc = 0.0;
-    for (int e = e0 + row; e < e1; e += 16) {
+    for (int e = blockIdx.x * 64 + row; e < d.E; e += 64 * gridDim.x) {
         acc += (double)s.stats[(size_t)e * RISVEC_NSTAT + col];
         if (col == 0) racc += (double)s.reward[e];
     }
-    // reduce over the 16 rows: lanes l and l ^ 16 hold the same column in one warp
-    acc += __shfl_xor_sync(kFull, acc, 16);
-    racc += __shfl_xor_sync(kFull, racc, 16);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane < 16) red[warp][lane] = acc;
-    if (lane == 0) red[warp][RISVEC_NSTAT] = racc;
+    red[row][col] = acc;
+    if (col == 0) red[row][RISVEC_NSTAT] = racc;
     __syncthreads();
-    if (threadIdx.x <= RISVEC_NSTAT) {
-        double v = 0.0;
-        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-        atomicAdd(out + threadIdx.x, v);
+    for (int half = 32; half > 0; half >>= 1) {
+        if (row < half) {
+            red[row][col] += red[row + half][col];
+            if (col == 0) red[row][RISVEC_NSTAT] += red[row + half][RISVEC_NSTAT];
+        }
+        __syncthreads();
     }
+    if (threadIdx.x <= RISVEC_NSTAT) atomicAdd(out + threadIdx.x, red[0][threadIdx.x]);
 }
 
 }  // namespace
@@ -808,12 +806,12 @@ int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float
     return check_launch(env, "k_map_actions_sarl");
 }
 
-int risvec_shard_stats(risvec_env_t* env, double* out, void* stream) {
+int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream) {
     if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(env->device));
-    CUDA_TRY(cudaMemsetAsync(out, 0, (RISVEC_NSTAT + 1) * sizeof(double), (cudaStream_t)stream));
-    const int blocks = env->dims.E >= 2048 ? 32 : (env->dims.E + 63) / 64;
-    k_shard_stats<<<blocks, 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
+    if (!accumulate) CUDA_TRY(cudaMemsetAsync(out, 0, (RISVEC_NSTAT + 1) * sizeof(double), (cudaStream_t)stream));
+    const int blocks = env->dims.E >= 1024 ? 16 : (env->dims.E + 63) / 64;
+    k_shard_stats<<<blocks, 1024, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
     return check_launch(env, "k_shard_stats");
 }
 

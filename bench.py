@@ -380,6 +380,11 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
+        if wl == "sarl":
+            kernel_name = ("k_sarl_v8<%d,true,true,true> (packed records)" % (M // 8)) if packed else (
+                "k_sarl_v8" if (V <= 8 and M <= 40) else "k_sarl_rollout")
+        else:
+            kernel_name = "k_marl_v8<true,false>" if V <= 8 else "k_marl_rollout"
         alg = algorithmic_bytes(wl, V, M, T, E)
         achieved = alg / (kern_ms_avg * 1e-3) / 1e9
         line = {
@@ -391,7 +396,8 @@ def main():
                     "steps": args.e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(wl), "kernel": f"k_{wl}_rollout", "peak_source": peak_src,
+                         "traffic": recorded_traffic(wl) if (E, V, M, T) == (4096, 8, 40, 256) else None,
+                         "kernel": kernel_name, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "kernel_ms_avg": kern_ms_avg,
                          "kernel_ms_min": kern_ms[0], "env_steps_per_launch": E * T},
         }

@@ -689,9 +689,10 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
     if constexpr (PACKED) {
         pf_base = (const char*)(a.in_rec + grp * (4 * RIN)) + 32 * lane;
         pf_stride = (size_t)sIn * 4;
-        pf_on = lane < (4 * RIN * 4 + 31) / 32;
+        pf_on = lane < (4 * RIN * 4) / 32;  // whole sectors of the slab only: never past the buffer
     } else {
-        const int n_ph = (4 * M * 4 + 31) / 32, n_ac = (4 * 2 * V * 4 + 31) / 32, n_ar = (4 * V * 4 + 31) / 32;
+        // whole sectors of each slab only, so a prefetch never points past the end of a buffer
+        const int n_ph = (4 * M * 4) / 32, n_ac = (4 * 2 * V * 4) / 32, n_ar = (4 * V * 4) / 32;
         if (lane < n_ph) {
             pf_base = (const char*)(a.phase + (size_t)e0 * M) + 32 * lane;
             pf_stride = (size_t)sM * 4;

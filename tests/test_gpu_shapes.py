@@ -89,3 +89,46 @@ def test_marl_random_shapes(V, M):
         close(got["DataBuf"][t], o.DataBuf, 1e-5, f"DataBuf t={t}")
         close(np.where(band, 0, got["reward_user"][t]), np.where(band, 0, r_user), 2e-6, f"reward_user t={t}")
         close(got["stats"][t][:, 0], L["delay_mean"], 1e-9 + 1e-3 * band.any(axis=1), f"delay_mean t={t}")
+
+
+@pytest.mark.parametrize("variant,V,M,E,T", [("sarl", 8, 40, 4098, 7), ("sarl", 5, 33, 9, 4), ("sarl", 32, 256, 3, 5),
+                                             ("sarl", 17, 100, 5, 3), ("marl", 8, 40, 4097, 6), ("marl", 6, 7, 10, 5),
+                                             ("marl", 32, 64, 3, 4)])
+def test_traces_stay_inside_their_buffers(variant, V, M, E, T):
+    """compute-sanitizer is not available on this pool, so bounds are checked with canaries:
+    every trace is carved out of a sentinel-filled arena with guard bands on both sides; after a
+    rollout each trace must be fully written (no sentinel left) and every guard band intact."""
+    from ris_vec_marl_b200 import BatchedEnviron, MARL_TRACES, SARL_TRACES, marl_yaml_overrides
+
+    over = marl_yaml_overrides() if variant == "marl" else {}
+    env = BatchedEnviron(variant, E, V, M, **over)
+    env.make_new_game(); env.renew_positions(); env.compute_parms()
+    names = SARL_TRACES if variant == "sarl" else MARL_TRACES
+    shapes = {k: tuple(v.shape) for k, v in env._alloc_traces(names, T, names).items()}
+    guard, sentinel = 1024, -7.0e30
+    total = sum(int(np.prod(sh)) + guard for sh in shapes.values()) + guard
+    arena = torch.full((total,), sentinel, dtype=torch.float32, device="cuda")
+    out, off = {}, guard
+    for k, sh in shapes.items():
+        n = int(np.prod(sh))
+        out[k] = arena[off:off + n].view(sh)
+        off += n + guard
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    acts = torch.rand(T, E, 2, V, device="cuda", generator=gen)
+    arr = torch.poisson(torch.full((T, E, V), 2.0, device="cuda"), generator=gen).to(torch.int32)
+    if variant == "sarl":
+        env.rollout_sarl(acts, torch.rand(T, E, M, device="cuda", generator=gen) * 6.28, arr, out=out)
+    else:
+        env.optimize_phase_shift(); env.update_channel_gains()
+        part = torch.full((E, V), -1, dtype=torch.int32, device="cuda")
+        env.rollout_marl(acts, part, torch.full((E,), V, dtype=torch.int32, device="cuda"), arr, out=out)
+    torch.cuda.synchronize()
+    mask = torch.ones(total, dtype=torch.bool, device="cuda")
+    off = guard
+    for k, sh in shapes.items():
+        n = int(np.prod(sh))
+        mask[off:off + n] = False
+        assert not (out[k] == sentinel).any(), f"{k} not fully written"
+        assert torch.isfinite(out[k]).all(), k
+        off += n + guard
+    assert (arena[mask] == sentinel).all(), "a kernel wrote outside its trace buffers"

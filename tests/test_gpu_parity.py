@@ -290,3 +290,62 @@ def test_observation_and_action_mapping_match_the_driver_formulas():
                                          f("vehicle_rate") / 20], -1)], axis=-1)
     np.testing.assert_allclose(obs, want, rtol=1e-6, atol=1e-7)
     assert obs.reshape(E, -1).shape[1] == 80  # the DDPG input size of ddpg_train.py:75
+
+
+@pytest.mark.parametrize("model,K_dB", [("3gpp_umi", 0.0), ("3gpp_uma", 0.0), ("3gpp_umi", 6.0), ("bogus", 0.0)])
+def test_3gpp_channel_branch_matches_oracle(model, K_dB):
+    """update_channel_gains for channel_model != "free" (MARL/Environment.py:275-327) with injected
+    LOS / shadowing / small-scale draws; an unknown keyword falls back to path loss 0 dB (:315-317)."""
+    from oracle.env_oracle import EnvOracle, InjectedDraws, OracleParams
+    from ris_vec_marl_b200 import BatchedEnviron
+
+    E, V, M = 37, 8, 40
+    rng = np.random.default_rng(9)
+    pat = [(0, 4), (220, 230), (10, 15), (170, 180), (10, 15), (220, 230), (10, 15), (170, 180), (10, 15)] * 2 + [(5, 9)]
+    ints = np.stack([rng.integers(lo, hi, E) for lo, hi in pat], axis=1).astype(np.int32)
+    c_rand, c_norm, c_exp = rng.random((E, V)), rng.standard_normal((E, V, 3)), rng.exponential(1.0, (E, V))
+    env = BatchedEnviron("marl", E, V, M, channel_model=model, rician_K_dB=K_dB)
+    env.make_new_game(ints)
+    env.update_channel_gains(c_rand, c_norm, c_exp)
+    p = OracleParams()
+    p.channel_model, p.rician_K_dB = model, K_dB
+    d = InjectedDraws(reset_ints=ints)
+    o = EnvOracle("marl", V, M, 3, E=E, params=p, draws=d)
+    o.make_new_game()
+    # the oracle pops per vehicle: rand, normal, then exponential or two more normals
+    n_norm = 1 if K_dB <= 1e-6 else 3
+    d.set_channel_draws(c_rand, c_norm[:, :, :n_norm].reshape(E, -1), c_exp)
+    o.update_channel_gains()
+    np.testing.assert_allclose(env.gains.cpu().numpy(), o.channel_gains, rtol=1e-11)
+    # on-device Philox draws: finite, positive, reproducible per (seed, env index)
+    env.update_channel_gains()
+    g1 = env.gains.clone()
+    assert torch.isfinite(g1).all() and (g1 > 0).all()
+
+
+def test_checkpoint_roundtrip_and_attribute_writes():
+    """state_dict / load_state_dict resume bit-exactly; parameter writes between episodes
+    (marl_train_bcd.py:563-594) take effect on the next launch."""
+    from ris_vec_marl_b200 import BatchedEnviron, marl_yaml_overrides
+
+    E, V, M, T = 64, 8, 40, 10
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    acts = torch.rand(2 * T, E, 2, V, device="cuda", generator=gen)
+    part = torch.full((E, V), -1, dtype=torch.int32, device="cuda")
+    ng = torch.full((E,), V, dtype=torch.int32, device="cuda")
+    a = BatchedEnviron("marl", E, V, M, seed=3, **marl_yaml_overrides())
+    a.make_new_game(); a.renew_positions(); a.compute_parms(); a.optimize_phase_shift(); a.update_channel_gains()
+    a.rollout_marl(acts[:T], part, ng)
+    sd = a.state_dict()
+    ref = a.rollout_marl(acts[T:], part, ng)
+    b = BatchedEnviron("marl", E, V, M, seed=3, **marl_yaml_overrides())
+    b.load_state_dict(sd)
+    got = b.rollout_marl(acts[T:], part, ng)  # on-device arrivals continue from the restored step counters
+    for k in ref:
+        assert torch.equal(ref[k], got[k]), k
+    b.load_state_dict(sd)
+    b.set_params(w_d=2.0, w_e=0.0, qos_penalty=0.0)
+    got2 = b.rollout_marl(acts[T:], part, ng)
+    assert torch.equal(got2["rate"], ref["rate"]) and not torch.equal(got2["reward_user"], ref["reward_user"])
+    want = -(2.0 * b.stats[:, 0])  # reward = -(w_d * delay) when w_e = 0 and no QoS penalty
+    np.testing.assert_allclose(b.reward.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-7)

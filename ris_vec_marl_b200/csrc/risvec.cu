@@ -59,6 +59,8 @@ struct risvec_env {
     // device staging for the *_host entry points (grow-only) + their copy pipeline
     char* stage;
     size_t stage_bytes;
+    char* scratch;  // |S|^2 hand-over between the cascade and scan kernels (grow-only)
+    size_t scratch_bytes;
     int pipe_ready;
     cudaStream_t s_in, s_out;
     cudaEvent_t ev[2 * 16 + 2];
@@ -120,16 +122,44 @@ int launch_marl(risvec_env* env, const MarlArgs& a, cudaStream_t st) {
     return check_launch(env, "k_marl_rollout");
 }
 
+int ensure_scratch(risvec_env* env, size_t bytes) {
+    if (bytes <= env->scratch_bytes) return RISVEC_OK;
+    if (env->scratch) cudaFree(env->scratch);
+    env->scratch = nullptr;
+    env->scratch_bytes = 0;
+    CUDA_TRY(cudaMalloc((void**)&env->scratch, bytes));
+    env->scratch_bytes = bytes;
+    return RISVEC_OK;
+}
+
 template <int VP, int MPL, int WPE>
-int launch_sarl_cfg(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
+int launch_sarl_cfg(risvec_env* env, const SarlArgs& a_in, cudaStream_t st) {
     constexpr int EPW = 32 / VP;
-    const int blocks = (env->dims.E + EPW - 1) / EPW;
-    const size_t MS = (size_t)((env->dims.M + 2 * WPE + 3) / 2) * 2;  // must match the kernel
+    SarlArgs a = a_in;
+    const int E = env->dims.E, V = env->dims.V;
+    const int blocks = (E + EPW - 1) / EPW;
+    const size_t MS = (size_t)((env->dims.M + 4 * WPE + 7) / 4) * 4;  // must match the kernel
     const size_t smem = 6 * EPW * MS * sizeof(float) + (WPE > 1 ? 2 * WPE * 32 * sizeof(float2) : 0);
-    auto kern = k_sarl_rollout<VP, MPL, WPE>;
+    if (WPE == 1) {  // one warp per env group: fused step kernel
+        auto kern = k_sarl_rollout<VP, MPL, WPE, false>;
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, 32 * WPE, smem, st>>>(env->dims, env->st, env->params, a);
+        return check_launch(env, "k_sarl_rollout");
+    }
+    // several warps per env (large M): cascade kernel over (env group, time chunk) -> |S|^2 scratch,
+    // then the per-vehicle scan kernel
+    if (int rc = ensure_scratch(env, (size_t)a.T * E * V * sizeof(float))) return rc;
+    a.g2 = (float*)env->scratch;
+    int chunk = 32;
+    while (chunk > 2 && (long long)blocks * ((a.T + chunk - 1) / chunk) < 4 * 148) chunk >>= 1;  // fill the SMs
+    a.t_chunk = chunk;
+    auto kern = k_sarl_rollout<VP, MPL, WPE, true>;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, 32 * WPE, smem, st>>>(env->dims, env->st, env->params, a);
-    return check_launch(env, "k_sarl_rollout");
+    kern<<<dim3(blocks, (a.T + chunk - 1) / chunk), 32 * WPE, smem, st>>>(env->dims, env->st, env->params, a);
+    if (int rc = check_launch(env, "k_sarl_rollout<cascade>")) return rc;
+    const long long total = (long long)E * VP;
+    k_sarl_scan<VP><<<(int)((total + 127) / 128), 128, 0, st>>>(env->dims, env->st, env->params, a);
+    return check_launch(env, "k_sarl_scan");
 }
 
 template <int MPI>
@@ -318,6 +348,7 @@ int risvec_destroy(risvec_env_t* env) {
     cudaSetDevice(env->device);
     if (env->arena) cudaFree(env->arena);
     if (env->stage) cudaFree(env->stage);
+    if (env->scratch) cudaFree(env->scratch);
     if (env->pipe_ready) {
         cudaStreamDestroy(env->s_in);
         cudaStreamDestroy(env->s_out);

@@ -33,6 +33,8 @@ struct SarlArgs {
     risvec_sarl_out_t out;
     const float* in_rec;  // packed layout: [T,E,24 + M]  (see include/risvec.h)
     float* out_rec;       // packed layout: [T,E,RISVEC_SARL_OUT_WORDS]
+    float* g2;            // [T,E,V] scratch |S_v|^2 between the cascade and scan kernels (large M)
+    int t_chunk;          // steps per block of the cascade kernel (even)
 };
 
 __device__ inline int draw_arrival(const Dims& d, int e, int v, long long step, float lam) {
@@ -333,17 +335,21 @@ __device__ __forceinline__ double2 cpow64(double2 z, unsigned n) {  // z^n by sq
     return r;
 }
 
-template <int VP, int MPL, int WPE>
+// CASCADE = true: the kernel only produces |S_v|^2 for the steps [blockIdx.y * t_chunk, +t_chunk)
+// into a.g2 (no state is touched except phase_real of the last step); k_sarl_scan finishes the
+// steps.  Used when several warps share an env (large M): the per-vehicle phase would otherwise
+// be a serial section of one warp per block and step, and splitting also exposes T-parallelism.
+template <int VP, int MPL, int WPE, bool CASCADE>
 __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
-    static_assert(MPL % 2 == 0, "elements are processed in FFMA2 pairs");
+    static_assert(MPL % 4 == 0, "elements are processed four at a time (LDS.128 + FFMA2 pairs)");
     constexpr int EPW = 32 / VP;  // envs per warp (= per block)
     constexpr int NT = 32 * WPE;
-    extern __shared__ float sarl_smem[];
+    extern __shared__ __align__(16) float sarl_smem[];
     const int E = d.E, V = d.V, M = d.M, T = a.T;
     // theta = exp(j*phase) of the block's envs as three planes (cos, sin, -sin) so that two
     // consecutive elements load as one float2 FFMA2 operand; double-buffered over steps.
-    // MS = padded plane stride (covers the odd-slice pad element, 8 B aligned pairs).
-    const int MS = ((M + 2 * WPE + 3) / 2) * 2;
+    // MS = padded plane stride (covers the pad elements of the last slice, 16 B aligned quads).
+    const int MS = ((M + 4 * WPE + 7) / 4) * 4;
     const int plane = EPW * MS;
     float* th = sarl_smem;                                              // [2][3][EPW][MS]
     float2* part = reinterpret_cast<float2*>(sarl_smem + 6 * plane);    // [2][WPE][32] (WPE > 1)
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
     const bool env_ok = e < E;
     const bool act = env_ok && v < V;
     const size_t ev = (size_t)e * V + v;
-    const int slice = (((M + WPE - 1) / WPE) + 1) & ~1;  // even slices keep the float2 pairs aligned
+    const int slice = (((M + WPE - 1) / WPE) + 3) & ~3;  // multiples of 4 keep the float4 quads aligned
     const int m0 = w * slice;
     const int m1 = min(M, m0 + slice);
 
@@ -375,7 +381,9 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
     }
     for (int i = threadIdx.x; i < 6 * plane; i += NT) th[i] = 0.f;  // pad elements must stay finite
     const bool cphase = (w == 0);
-    double buf = (act && cphase) ? s.databuf[ev] : 0.0;
+    const int t_begin = CASCADE ? (int)blockIdx.y * a.t_chunk : 0;
+    const int t_end = CASCADE ? min(T, t_begin + a.t_chunk) : T;
+    double buf = (!CASCADE && act && cphase) ? s.databuf[ev] : 0.0;
     const float coef = act ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
     const long long step0 = env_ok ? s.step_ctr[e] : 0;
 
@@ -401,18 +409,30 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
             pf1 = (int)threadIdx.x + NT < n_ph ? __ldg(ph_t + threadIdx.x + NT) : 0.f;
         }
     };
+    const int idxA = threadIdx.x, idxB = threadIdx.x + NT;  // my two elements of the first pass
+    const int offA = (idxA / M) * MS + idxA % M, offB = (idxB / M) * MS + idxB % M;
     auto produce_theta = [&](int t) {
         const float* ph_t = a.phase + ((size_t)t * E + e0) * M;
         float* c_pl = th + (t & 1) * 3 * plane;
         float* s_pl = c_pl + plane;
         float* n_pl = s_pl + plane;
-        for (int idx = threadIdx.x; idx < n_ph; idx += 2 * NT) {
-            const int idx2 = idx + NT;
-            const bool first = idx == (int)threadIdx.x;
-            const float ph0 = first ? pf0 : __ldg(ph_t + idx);
-            const float ph1 = first ? pf1 : (idx2 < n_ph ? __ldg(ph_t + idx2) : 0.f);
+        if ((threadIdx.x & 7) == 0 && (int)threadIdx.x < n_ph && t + 8 < T)  // one 32 B sector per 8 threads
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ph_t + (size_t)8 * E * M + threadIdx.x));
+        if (idxA < n_ph) {
             float2 sn, cs;
-            sincos_fast2(make_float2(ph0, ph1), &sn, &cs);  // SARL:125-131
+            sincos_fast2(make_float2(pf0, pf1), &sn, &cs);  // SARL:125-131
+            c_pl[offA] = cs.x; s_pl[offA] = sn.x; n_pl[offA] = -sn.x;
+            if (idxB < n_ph) { c_pl[offB] = cs.y; s_pl[offB] = sn.y; n_pl[offB] = -sn.y; }
+            if (t == T - 1) {
+                s.phase_real[(size_t)e0 * M + idxA] = pf0;
+                if (idxB < n_ph) s.phase_real[(size_t)e0 * M + idxB] = pf1;
+            }
+        }
+        for (int idx = threadIdx.x + 2 * NT; idx < n_ph; idx += 2 * NT) {  // only when n_ph > 2 * NT
+            const int idx2 = idx + NT;
+            const float ph0 = __ldg(ph_t + idx), ph1 = idx2 < n_ph ? __ldg(ph_t + idx2) : 0.f;
+            float2 sn, cs;
+            sincos_fast2(make_float2(ph0, ph1), &sn, &cs);
             const int ea = idx / M, ma = idx - ea * M;
             c_pl[ea * MS + ma] = cs.x; s_pl[ea * MS + ma] = sn.x; n_pl[ea * MS + ma] = -sn.x;
             if (idx2 < n_ph) {
@@ -429,7 +449,7 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
     float na0 = 0.f, na1 = 0.f;
     int narr = 0;
     auto fetch_scalars = [&](int t) {
-        if (cphase && act && t < T) {
+        if (!CASCADE && cphase && act && t < T) {
             const size_t ta = ((size_t)t * E + e) * 2 * V + v;
             na0 = __ldg(a.action + ta);
             na1 = __ldg(a.action + ta + V);
@@ -438,36 +458,42 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
     };
 
     __syncthreads();  // zero fill done
-    fetch_phase(0);
-    fetch_scalars(0);
-    if (T > 0) produce_theta(0);
-    fetch_phase(1);
+    fetch_phase(t_begin);
+    fetch_scalars(t_begin);
+    if (t_begin < t_end) produce_theta(t_begin);
+    fetch_phase(t_begin + 1);
     __syncthreads();
-    for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) produce_theta(t + 1);  // overlaps with this step's MACs (other buffer)
+    for (int t = t_begin; t < t_end; ++t) {
+        if (t + 1 < t_end) produce_theta(t + 1);  // overlaps with this step's MACs (other buffer)
         fetch_phase(t + 2);
         const float a0 = na0, a1 = na1;
         const int arr_in = narr;
         fetch_scalars(t + 1);
 
-        // (2) cascaded reduction over this warp's element slice, two elements per FFMA2
+        // (2) cascaded reduction over this warp's element slice: four elements per LDS.128 of each
+        // theta plane, two elements per FFMA2
         const float* c_pl = th + (t & 1) * 3 * plane + el * MS + m0;
-        const float2* c2 = reinterpret_cast<const float2*>(c_pl);
-        const float2* s2 = reinterpret_cast<const float2*>(c_pl + plane);
-        const float2* n2 = reinterpret_cast<const float2*>(c_pl + 2 * plane);
+        const float4* c4 = reinterpret_cast<const float4*>(c_pl);
+        const float4* s4 = reinterpret_cast<const float4*>(c_pl + plane);
+        const float4* n4 = reinterpret_cast<const float4*>(c_pl + 2 * plane);
         float2 REa = make_float2(0.f, 0.f), IMa = REa, REb = REa, IMb = REa;
+        auto quad = [&](int gq) {
+            const float4 tx = c4[gq], ty = s4[gq], nty = n4[gq];
+            const float2 txa = make_float2(tx.x, tx.y), txb = make_float2(tx.z, tx.w);
+            const float2 tya = make_float2(ty.x, ty.y), tyb = make_float2(ty.z, ty.w);
+            const float2 nya = make_float2(nty.x, nty.y), nyb = make_float2(nty.z, nty.w);
+            REa = __ffma2_rn(txa, WX[2 * gq], REa); REa = __ffma2_rn(nya, WY[2 * gq], REa);
+            IMa = __ffma2_rn(txa, WY[2 * gq], IMa); IMa = __ffma2_rn(tya, WX[2 * gq], IMa);
+            REb = __ffma2_rn(txb, WX[2 * gq + 1], REb); REb = __ffma2_rn(nyb, WY[2 * gq + 1], REb);
+            IMb = __ffma2_rn(txb, WY[2 * gq + 1], IMb); IMb = __ffma2_rn(tyb, WX[2 * gq + 1], IMb);
+        };
+        if (m1 - m0 == MPL) {  // full slice (warp-uniform): no per-quad guards
 #pragma unroll
-        for (int i = 0; i < MPL / 2; i += 2) {
-            if (m0 + 2 * i < m1) {
-                const float2 tx = c2[i], ty = s2[i], nty = n2[i];
-                REa = __ffma2_rn(tx, WX[i], REa); REa = __ffma2_rn(nty, WY[i], REa);
-                IMa = __ffma2_rn(tx, WY[i], IMa); IMa = __ffma2_rn(ty, WX[i], IMa);
-            }
-            if (i + 1 < MPL / 2 && m0 + 2 * (i + 1) < m1) {
-                const float2 tx = c2[i + 1], ty = s2[i + 1], nty = n2[i + 1];
-                REb = __ffma2_rn(tx, WX[i + 1], REb); REb = __ffma2_rn(nty, WY[i + 1], REb);
-                IMb = __ffma2_rn(tx, WY[i + 1], IMb); IMb = __ffma2_rn(ty, WX[i + 1], IMb);
-            }
+            for (int gq = 0; gq < MPL / 4; ++gq) quad(gq);
+        } else {
+#pragma unroll
+            for (int gq = 0; gq < MPL / 4; ++gq)
+                if (m0 + 4 * gq < m1) quad(gq);
         }
         float sr = (REa.x + REa.y) + (REb.x + REb.y);
         float si = (IMa.x + IMa.y) + (IMb.x + IMb.y);
@@ -487,6 +513,10 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
             __syncwarp();
         }
 
+        if constexpr (CASCADE) {
+            if (cphase && act) a.g2[((size_t)t * E + e) * V + v] = __fmaf_rn(sr, sr, __fmul_rn(si, si));
+            continue;
+        }
         // (3) per-vehicle queue update and reward (SARL:327-358), first warp of the block
         if (cphase) {
             const size_t tev = ((size_t)t * E + e) * V + v;
@@ -522,7 +552,87 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
         if (WPE == 1) __syncwarp();  // theta(t + 1) of this warp is complete before the next MACs
     }
 
-    if (cphase && act && T > 0) {
+    if (!CASCADE && cphase && act && T > 0) {
+        s.databuf[ev] = buf;
+        s.rate[ev] = o_rate;
+        s.data_t[ev] = o_dt;
+        s.data_p[ev] = o_dp;
+        s.over_power[ev] = o_overp;
+        s.over_data[ev] = o_overd;
+        s.data_r[ev] = o_arr;
+        if (v == 0) {
+            s.reward[e] = o_rew;
+            s.step_ctr[e] = step0 + T;
+        }
+    }
+}
+
+// Second half of the split SARL step for large M: per-vehicle queue update and reward
+// (SARL:327-358) from the |S_v|^2 the cascade kernel left in a.g2.  An env owns VP lanes of a
+// warp (lane = vehicle); inputs of step t + 1 are prefetched while step t computes.
+template <int VP>
+__global__ void __launch_bounds__(128) k_sarl_scan(Dims d, State s, risvec_params_t p, SarlArgs a) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = gtid / VP, v = gtid % VP;
+    const int E = d.E, V = d.V, T = a.T;
+    const bool env_ok = e < E;
+    const bool act = env_ok && v < V;
+    const size_t ev = (size_t)min(e, E - 1) * V + min(v, V - 1);
+    double buf = s.databuf[ev];
+    const float coef = (float)(s.amp[ev] / (kSigma * kSigma));  // SARL:157-159
+    const long long step0 = s.step_ctr[min(e, E - 1)];
+    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
+    const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);
+    const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));
+    const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
+    const float invV = 1.0f / (float)V;
+    const float lam = (float)p.rate;
+    const size_t sV = (size_t)E * V, s2V = 2 * sV;
+    const float* ac = a.action + (size_t)min(e, E - 1) * 2 * V + min(v, V - 1);
+    float na0 = 0.f, na1 = 0.f, ng2 = 0.f;
+    int narr = 0;
+    auto fetch = [&](int t) {
+        if (t < T) {
+            na0 = __ldg(ac + (size_t)t * s2V);
+            na1 = __ldg(ac + (size_t)t * s2V + V);
+            ng2 = __ldg(a.g2 + (size_t)t * sV + ev);
+            narr = a.arrivals != nullptr ? __ldg(a.arrivals + (size_t)t * sV + ev) : 0;
+        }
+    };
+    fetch(0);
+    float o_rate = 0.f, o_dt = 0.f, o_dp = 0.f, o_overp = 0.f, o_overd = 0.f, o_rew = 0.f;
+    int o_arr = 0;
+    for (int t = 0; t < T; ++t) {
+        const float a0 = na0, a1 = na1, g2 = ng2;
+        int arr = narr;
+        fetch(t + 1);
+        if (act && a.arrivals == nullptr) arr = draw_arrival(d, e, v, step0 + t, lam);
+        const float rate = log1p_sfu(__fmul_rn(a0, __fmul_rn(coef, g2)));  // natural log, SARL:159
+        const float data_t = __fmul_rn(rate, c_dt);
+        const float data_p = __fmul_rn(cbrt_sfu(a1), c_dp);
+        const double raw = __dsub_rn(buf, __dadd_rn((double)data_t, (double)data_p));  // SARL:334
+        const bool neg = raw < 0.0;
+        const float b = __fmul_rn((float)fmax(0.0, raw + (double)data_p), c_rev);
+        const float overp = neg ? __fsub_rn(a1, __fmul_rn(__fmul_rn(b, b), b)) : 0.f;  // SARL:336-339
+        const float overd = neg ? (float)(-raw) : 0.f;
+        const double nb = neg ? 0.0 : raw;
+        const float base = __fsub_rn(-__fmul_rn(t1, __fadd_rn(a0, a1)), __fmul_rn(t2, (float)nb));
+        const float pen = (nb > 0.0) ? pen1 : ((overd > 2.0f) ? pen2 : 0.f);  // SARL:343-352
+        const float rew = __fmul_rn(seg_sum<VP>(act ? __fsub_rn(base, pen) : 0.f), invV);
+        buf = __dadd_rn(nb, __dmul_rn(__dmul_rn((double)arr, p.time_fast), 1000.0));  // SARL:354-356
+        if (act) {
+            const size_t tev = (size_t)t * sV + ev;
+            if (a.out.DataBuf != nullptr) a.out.DataBuf[tev] = (float)buf;
+            if (a.out.data_t != nullptr) a.out.data_t[tev] = data_t;
+            if (a.out.data_p != nullptr) a.out.data_p[tev] = data_p;
+            if (a.out.over_power != nullptr) a.out.over_power[tev] = overp;
+            if (a.out.over_data != nullptr) a.out.over_data[tev] = overd;
+            if (a.out.rate != nullptr) a.out.rate[tev] = rate;
+            if (v == 0 && a.out.reward != nullptr) a.out.reward[(size_t)t * E + e] = rew;
+        }
+        o_rate = rate; o_dt = data_t; o_dp = data_p; o_overp = overp; o_overd = overd; o_rew = rew; o_arr = arr;
+    }
+    if (act && T > 0) {
         s.databuf[ev] = buf;
         s.rate[ev] = o_rate;
         s.data_t[ev] = o_dt;

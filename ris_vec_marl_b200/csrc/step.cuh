@@ -340,7 +340,7 @@ __device__ __forceinline__ double2 cpow64(double2 z, unsigned n) {  // z^n by sq
 // steps.  Used when several warps share an env (large M): the per-vehicle phase would otherwise
 // be a serial section of one warp per block and step, and splitting also exposes T-parallelism.
 template <int VP, int MPL, int WPE, bool CASCADE>
-__global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
+__global__ void __launch_bounds__(32 * WPE, (WPE > 1 && WPE <= 8 && MPL <= 32) ? 16 / WPE : 1) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
     static_assert(MPL % 4 == 0, "elements are processed four at a time (LDS.128 + FFMA2 pairs)");
     constexpr int EPW = 32 / VP;  // envs per warp (= per block)
     constexpr int NT = 32 * WPE;
@@ -400,32 +400,37 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
     int o_arr = 0;
 
     // theta(t) -> smem buffer t & 1: thread k handles elements k, k + NT, ... in packed pairs.
-    // The first pair of every step is prefetched one step ahead into (pf0, pf1).
+    // The first pair of every step is prefetched one step ahead into (pf0, pf1).  All stream
+    // addresses are running pointers bumped by one step stride (no per-step 64-bit index math).
+    const size_t stepM = (size_t)E * M;
+    const bool hasA = (int)threadIdx.x < n_ph, hasB = (int)threadIdx.x + NT < n_ph;
+    const float* fetch_ptr = a.phase + ((size_t)t_begin * E + e0) * M + threadIdx.x;  // step the next fetch reads
+    int fetch_t = t_begin;
     float pf0 = 0.f, pf1 = 0.f;
-    auto fetch_phase = [&](int t) {
-        if (t < T) {
-            const float* ph_t = a.phase + ((size_t)t * E + e0) * M;
-            pf0 = (int)threadIdx.x < n_ph ? __ldg(ph_t + threadIdx.x) : 0.f;
-            pf1 = (int)threadIdx.x + NT < n_ph ? __ldg(ph_t + threadIdx.x + NT) : 0.f;
+    auto fetch_phase = [&]() {  // loads step `fetch_t`, then moves on
+        if (fetch_t < T) {
+            pf0 = hasA ? __ldg(fetch_ptr) : 0.f;
+            pf1 = hasB ? __ldg(fetch_ptr + NT) : 0.f;
         }
+        fetch_ptr += stepM;
+        ++fetch_t;
     };
     const int idxA = threadIdx.x, idxB = threadIdx.x + NT;  // my two elements of the first pass
     const int offA = (idxA / M) * MS + idxA % M, offB = (idxB / M) * MS + idxB % M;
-    auto produce_theta = [&](int t) {
-        const float* ph_t = a.phase + ((size_t)t * E + e0) * M;
+    const bool l2_lane = (threadIdx.x & 7) == 0 && hasA;  // one 32 B sector per 8 threads
+    auto produce_theta = [&](int t, const float* ph_t) {  // ph_t = phase row of step t for this block
         float* c_pl = th + (t & 1) * 3 * plane;
         float* s_pl = c_pl + plane;
         float* n_pl = s_pl + plane;
-        if ((threadIdx.x & 7) == 0 && (int)threadIdx.x < n_ph && t + 8 < T)  // one 32 B sector per 8 threads
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ph_t + (size_t)8 * E * M + threadIdx.x));
-        if (idxA < n_ph) {
+        if (l2_lane && t + 8 < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(ph_t + 8 * stepM + threadIdx.x));
+        if (hasA) {
             float2 sn, cs;
             sincos_fast2(make_float2(pf0, pf1), &sn, &cs);  // SARL:125-131
             c_pl[offA] = cs.x; s_pl[offA] = sn.x; n_pl[offA] = -sn.x;
-            if (idxB < n_ph) { c_pl[offB] = cs.y; s_pl[offB] = sn.y; n_pl[offB] = -sn.y; }
+            if (hasB) { c_pl[offB] = cs.y; s_pl[offB] = sn.y; n_pl[offB] = -sn.y; }
             if (t == T - 1) {
                 s.phase_real[(size_t)e0 * M + idxA] = pf0;
-                if (idxB < n_ph) s.phase_real[(size_t)e0 * M + idxB] = pf1;
+                if (hasB) s.phase_real[(size_t)e0 * M + idxB] = pf1;
             }
         }
         for (int idx = threadIdx.x + 2 * NT; idx < n_ph; idx += 2 * NT) {  // only when n_ph > 2 * NT
@@ -458,14 +463,18 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
     };
 
     __syncthreads();  // zero fill done
-    fetch_phase(t_begin);
+    const float* row = a.phase + ((size_t)t_begin * E + e0) * M;  // phase row of the step being produced
+    float* g2_ptr = CASCADE ? a.g2 + ((size_t)t_begin * E + e) * V + v : nullptr;
+    fetch_phase();
     fetch_scalars(t_begin);
-    if (t_begin < t_end) produce_theta(t_begin);
-    fetch_phase(t_begin + 1);
+    if (t_begin < t_end) produce_theta(t_begin, row);
+    row += stepM;
+    fetch_phase();
     __syncthreads();
     for (int t = t_begin; t < t_end; ++t) {
-        if (t + 1 < t_end) produce_theta(t + 1);  // overlaps with this step's MACs (other buffer)
-        fetch_phase(t + 2);
+        if (t + 1 < t_end) produce_theta(t + 1, row);  // overlaps with this step's MACs (other buffer)
+        row += stepM;
+        fetch_phase();
         const float a0 = na0, a1 = na1;
         const int arr_in = narr;
         fetch_scalars(t + 1);
@@ -514,7 +523,8 @@ __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risv
         }
 
         if constexpr (CASCADE) {
-            if (cphase && act) a.g2[((size_t)t * E + e) * V + v] = __fmaf_rn(sr, sr, __fmul_rn(si, si));
+            if (cphase && act) *g2_ptr = __fmaf_rn(sr, sr, __fmul_rn(si, si));
+            g2_ptr += (size_t)E * V;
             continue;
         }
         // (3) per-vehicle queue update and reward (SARL:327-358), first warp of the block

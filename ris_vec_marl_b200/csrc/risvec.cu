@@ -141,7 +141,7 @@ int launch_sarl_cfg(risvec_env* env, const SarlArgs& a_in, cudaStream_t st) {
     const size_t MS = (size_t)((env->dims.M + 4 * WPE + 7) / 4) * 4;  // must match the kernel
     const size_t smem = 6 * EPW * MS * sizeof(float) + (WPE > 1 ? 2 * WPE * 32 * sizeof(float2) : 0);
     if (WPE == 1) {  // one warp per env group: fused step kernel
-        auto kern = k_sarl_rollout<VP, MPL, WPE, false>;
+        auto kern = k_sarl_rollout<VP, MPL, WPE>;
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, 32 * WPE, smem, st>>>(env->dims, env->st, env->params, a);
         return check_launch(env, "k_sarl_rollout");
@@ -153,10 +153,14 @@ int launch_sarl_cfg(risvec_env* env, const SarlArgs& a_in, cudaStream_t st) {
     int chunk = 32;
     while (chunk > 2 && (long long)blocks * ((a.T + chunk - 1) / chunk) < 4 * 148) chunk >>= 1;  // fill the SMs
     a.t_chunk = chunk;
-    auto kern = k_sarl_rollout<VP, MPL, WPE, true>;
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(blocks, (a.T + chunk - 1) / chunk), 32 * WPE, smem, st>>>(env->dims, env->st, env->params, a);
-    if (int rc = check_launch(env, "k_sarl_rollout<cascade>")) return rc;
+    if constexpr (WPE > 1) {
+        const size_t smem2 = 12 * EPW * MS * sizeof(float) + 4 * WPE * 32 * sizeof(float2);
+        auto kern = k_sarl_cascade2<VP, MPL, WPE>;
+        if (smem2 > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        kern<<<dim3(blocks, (a.T + chunk - 1) / chunk), 32 * WPE, smem2, st>>>(env->dims, env->st, a);
+        if (int rc = check_launch(env, "k_sarl_cascade2")) return rc;
+    }
     const long long total = (long long)E * VP;
     k_sarl_scan<VP><<<(int)((total + 127) / 128), 128, 0, st>>>(env->dims, env->st, env->params, a);
     return check_launch(env, "k_sarl_scan");

@@ -335,12 +335,11 @@ __device__ __forceinline__ double2 cpow64(double2 z, unsigned n) {  // z^n by sq
     return r;
 }
 
-// CASCADE = true: the kernel only produces |S_v|^2 for the steps [blockIdx.y * t_chunk, +t_chunk)
-// into a.g2 (no state is touched except phase_real of the last step); k_sarl_scan finishes the
-// steps.  Used when several warps share an env (large M): the per-vehicle phase would otherwise
-// be a serial section of one warp per block and step, and splitting also exposes T-parallelism.
-template <int VP, int MPL, int WPE, bool CASCADE>
-__global__ void __launch_bounds__(32 * WPE, (WPE > 1 && WPE <= 8 && MPL <= 32) ? 16 / WPE : 1) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
+// Used when ONE warp serves an env group (M <= 40); larger M goes through k_sarl_cascade2 +
+// k_sarl_scan below (several warps per env: the per-vehicle phase would be a serial section of
+// one warp per block and step).
+template <int VP, int MPL, int WPE>
+__global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
     static_assert(MPL % 4 == 0, "elements are processed four at a time (LDS.128 + FFMA2 pairs)");
     constexpr int EPW = 32 / VP;  // envs per warp (= per block)
     constexpr int NT = 32 * WPE;
@@ -381,9 +380,8 @@ __global__ void __launch_bounds__(32 * WPE, (WPE > 1 && WPE <= 8 && MPL <= 32) ?
     }
     for (int i = threadIdx.x; i < 6 * plane; i += NT) th[i] = 0.f;  // pad elements must stay finite
     const bool cphase = (w == 0);
-    const int t_begin = CASCADE ? (int)blockIdx.y * a.t_chunk : 0;
-    const int t_end = CASCADE ? min(T, t_begin + a.t_chunk) : T;
-    double buf = (!CASCADE && act && cphase) ? s.databuf[ev] : 0.0;
+    const int t_begin = 0, t_end = T;
+    double buf = (act && cphase) ? s.databuf[ev] : 0.0;
     const float coef = act ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
     const long long step0 = env_ok ? s.step_ctr[e] : 0;
 
@@ -454,7 +452,7 @@ __global__ void __launch_bounds__(32 * WPE, (WPE > 1 && WPE <= 8 && MPL <= 32) ?
     float na0 = 0.f, na1 = 0.f;
     int narr = 0;
     auto fetch_scalars = [&](int t) {
-        if (!CASCADE && cphase && act && t < T) {
+        if (cphase && act && t < T) {
             const size_t ta = ((size_t)t * E + e) * 2 * V + v;
             na0 = __ldg(a.action + ta);
             na1 = __ldg(a.action + ta + V);
@@ -464,7 +462,6 @@ __global__ void __launch_bounds__(32 * WPE, (WPE > 1 && WPE <= 8 && MPL <= 32) ?
 
     __syncthreads();  // zero fill done
     const float* row = a.phase + ((size_t)t_begin * E + e0) * M;  // phase row of the step being produced
-    float* g2_ptr = CASCADE ? a.g2 + ((size_t)t_begin * E + e) * V + v : nullptr;
     fetch_phase();
     fetch_scalars(t_begin);
     if (t_begin < t_end) produce_theta(t_begin, row);
@@ -522,11 +519,6 @@ __global__ void __launch_bounds__(32 * WPE, (WPE > 1 && WPE <= 8 && MPL <= 32) ?
             __syncwarp();
         }
 
-        if constexpr (CASCADE) {
-            if (cphase && act) *g2_ptr = __fmaf_rn(sr, sr, __fmul_rn(si, si));
-            g2_ptr += (size_t)E * V;
-            continue;
-        }
         // (3) per-vehicle queue update and reward (SARL:327-358), first warp of the block
         if (cphase) {
             const size_t tev = ((size_t)t * E + e) * V + v;
@@ -562,7 +554,7 @@ __global__ void __launch_bounds__(32 * WPE, (WPE > 1 && WPE <= 8 && MPL <= 32) ?
         if (WPE == 1) __syncwarp();  // theta(t + 1) of this warp is complete before the next MACs
     }
 
-    if (!CASCADE && cphase && act && T > 0) {
+    if (cphase && act && T > 0) {
         s.databuf[ev] = buf;
         s.rate[ev] = o_rate;
         s.data_t[ev] = o_dt;
@@ -573,6 +565,147 @@ __global__ void __launch_bounds__(32 * WPE, (WPE > 1 && WPE <= 8 && MPL <= 32) ?
         if (v == 0) {
             s.reward[e] = o_rew;
             s.step_ctr[e] = step0 + T;
+        }
+    }
+}
+
+// Cascade kernel for several warps per env (large M), two steps per barrier: a block serves one
+// env group for a chunk of steps and only produces |S_v|^2 (a.g2).  Per pair of steps every
+// thread evaluates theta = exp(j*phase) of its element(s) for BOTH steps in one packed sin/cos,
+// every warp runs its element slice against both steps' theta planes (the phasor table in
+// registers is read once per pair), and one __syncthreads per pair publishes the partial sums
+// that the first warp folds over the WPE warps.  theta planes and partial sums are
+// double-buffered over pairs.
+template <int VP, int MPL, int WPE>
+__global__ void __launch_bounds__(32 * WPE, (WPE <= 8 && MPL <= 32) ? 16 / WPE : 1)
+    k_sarl_cascade2(Dims d, State s, SarlArgs a) {
+    static_assert(MPL % 4 == 0 && WPE > 1, "");
+    constexpr int EPW = 32 / VP;
+    constexpr int NT = 32 * WPE;
+    extern __shared__ __align__(16) float sarl_smem[];
+    const int E = d.E, V = d.V, M = d.M, T = a.T;
+    const int MS = ((M + 4 * WPE + 7) / 4) * 4;
+    const int plane = EPW * MS;
+    float* th = sarl_smem;                                               // [2 bufs][2 steps][3 planes][EPW][MS]
+    float2* part = reinterpret_cast<float2*>(sarl_smem + 12 * plane);    // [2 bufs][2 steps][WPE][32]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int el = lane / VP, v = lane % VP;
+    const int e0 = blockIdx.x * EPW, e = e0 + el;
+    const bool act = e < E && v < V;
+    const size_t ev = (size_t)e * V + v;
+    const int slice = (((M + WPE - 1) / WPE) + 3) & ~3;
+    const int m0 = w * slice, m1 = min(M, m0 + slice);
+
+    float2 WX[MPL / 2], WY[MPL / 2];
+    {
+        const double2 z = unit_phasor64(act ? d.angle_BR - s.angle[ev] : 0.0);
+        double2 wv = cpow64(z, (unsigned)m0);
+#pragma unroll
+        for (int i = 0; i < MPL; ++i) {
+            const bool on = act && (m0 + i < m1);
+            const float re = on ? (float)wv.x : 0.f, im = on ? (float)wv.y : 0.f;
+            if (i & 1) { WX[i >> 1].y = re; WY[i >> 1].y = im; }
+            else       { WX[i >> 1].x = re; WY[i >> 1].x = im; }
+            wv = cmul64(wv, z);
+        }
+    }
+    for (int i = threadIdx.x; i < 12 * plane; i += NT) th[i] = 0.f;  // pad elements must stay finite
+    const int t_begin = (int)blockIdx.y * a.t_chunk, t_end = min(T, t_begin + a.t_chunk);
+    const int n_ph = min(EPW, E - e0) * M;
+    const size_t stepM = (size_t)E * M;
+
+    // element(s) of this thread: idx = tid, tid + NT, ...; the first one is register-prefetched
+    const bool has0 = (int)threadIdx.x < n_ph;
+    const int off0 = ((int)threadIdx.x / M) * MS + (int)threadIdx.x % M;
+    const float* row = a.phase + ((size_t)t_begin * E + e0) * M;  // phase row of the pair being produced
+    float pfa = 0.f, pfb = 0.f;                                   // phases of (step, step + 1) for element tid
+    auto fetch_pair = [&](const float* r, int t) {
+        pfa = (has0 && t < T) ? __ldg(r + threadIdx.x) : 0.f;
+        pfb = (has0 && t + 1 < T) ? __ldg(r + stepM + threadIdx.x) : 0.f;
+    };
+    auto produce_pair = [&](int t, const float* r, int bufi) {  // theta of steps (t, t + 1) -> buffer bufi
+        float* b0 = th + bufi * 6 * plane;
+        float* b1 = b0 + 3 * plane;
+        if (has0) {
+            float2 sn, cs;
+            sincos_fast2(make_float2(pfa, pfb), &sn, &cs);  // SARL:125-131
+            b0[off0] = cs.x; b0[plane + off0] = sn.x; b0[2 * plane + off0] = -sn.x;
+            b1[off0] = cs.y; b1[plane + off0] = sn.y; b1[2 * plane + off0] = -sn.y;
+            if (t == T - 1) s.phase_real[(size_t)e0 * M + threadIdx.x] = pfa;
+            if (t + 1 == T - 1) s.phase_real[(size_t)e0 * M + threadIdx.x] = pfb;
+        }
+        for (int idx = threadIdx.x + NT; idx < n_ph; idx += NT) {  // only when n_ph > NT
+            const float pa = __ldg(r + idx), pb = (t + 1 < T) ? __ldg(r + stepM + idx) : 0.f;
+            float2 sn, cs;
+            sincos_fast2(make_float2(pa, pb), &sn, &cs);
+            const int o = (idx / M) * MS + idx % M;
+            b0[o] = cs.x; b0[plane + o] = sn.x; b0[2 * plane + o] = -sn.x;
+            b1[o] = cs.y; b1[plane + o] = sn.y; b1[2 * plane + o] = -sn.y;
+            if (t == T - 1) s.phase_real[(size_t)e0 * M + idx] = pa;
+            if (t + 1 == T - 1) s.phase_real[(size_t)e0 * M + idx] = pb;
+        }
+    };
+
+    __syncthreads();
+    fetch_pair(row, t_begin);
+    if (t_begin < t_end) produce_pair(t_begin, row, 0);
+    row += 2 * stepM;
+    fetch_pair(row, t_begin + 2);
+    __syncthreads();
+    float* g2_ptr = a.g2 + ((size_t)t_begin * E + e) * V + v;
+    const size_t sEV = (size_t)E * V;
+    int bufi = 0;
+    for (int t = t_begin; t < t_end; t += 2, bufi ^= 1) {
+        if (t + 2 < t_end) produce_pair(t + 2, row, bufi ^ 1);
+        row += 2 * stepM;
+        fetch_pair(row, t + 4);
+
+        const float* base = th + bufi * 6 * plane + el * MS + m0;
+        float2 RE[2][2], IM[2][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) RE[u][0] = RE[u][1] = IM[u][0] = IM[u][1] = make_float2(0.f, 0.f);
+        auto quad = [&](int gq) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float4* c4 = reinterpret_cast<const float4*>(base + u * 3 * plane);
+                const float4 tx = c4[gq];
+                const float4 ty = reinterpret_cast<const float4*>(base + u * 3 * plane + plane)[gq];
+                const float4 ny = reinterpret_cast<const float4*>(base + u * 3 * plane + 2 * plane)[gq];
+                const float2 txa = make_float2(tx.x, tx.y), txb = make_float2(tx.z, tx.w);
+                const float2 tya = make_float2(ty.x, ty.y), tyb = make_float2(ty.z, ty.w);
+                const float2 nya = make_float2(ny.x, ny.y), nyb = make_float2(ny.z, ny.w);
+                RE[u][0] = __ffma2_rn(txa, WX[2 * gq], RE[u][0]); RE[u][0] = __ffma2_rn(nya, WY[2 * gq], RE[u][0]);
+                IM[u][0] = __ffma2_rn(txa, WY[2 * gq], IM[u][0]); IM[u][0] = __ffma2_rn(tya, WX[2 * gq], IM[u][0]);
+                RE[u][1] = __ffma2_rn(txb, WX[2 * gq + 1], RE[u][1]); RE[u][1] = __ffma2_rn(nyb, WY[2 * gq + 1], RE[u][1]);
+                IM[u][1] = __ffma2_rn(txb, WY[2 * gq + 1], IM[u][1]); IM[u][1] = __ffma2_rn(tyb, WX[2 * gq + 1], IM[u][1]);
+            }
+        };
+        if (m1 - m0 == MPL) {
+#pragma unroll
+            for (int gq = 0; gq < MPL / 4; ++gq) quad(gq);
+        } else {
+#pragma unroll
+            for (int gq = 0; gq < MPL / 4; ++gq)
+                if (m0 + 4 * gq < m1) quad(gq);
+        }
+        float2* pt = part + bufi * 2 * WPE * 32;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            pt[(u * WPE + w) * 32 + lane] = make_float2((RE[u][0].x + RE[u][0].y) + (RE[u][1].x + RE[u][1].y),
+                                                        (IM[u][0].x + IM[u][0].y) + (IM[u][1].x + IM[u][1].y));
+        __syncthreads();  // partial sums of this pair + theta of the next pair are complete
+        if (w == 0) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float sr = 0.f, si = 0.f;
+#pragma unroll
+                for (int k = 0; k < WPE; ++k) {
+                    const float2 q = pt[(u * WPE + k) * 32 + lane];
+                    sr += q.x; si += q.y;
+                }
+                if (act && t + u < t_end) g2_ptr[u * sEV] = __fmaf_rn(sr, sr, __fmul_rn(si, si));
+            }
+            g2_ptr += 2 * sEV;
         }
     }
 }
@@ -599,23 +732,39 @@ __global__ void __launch_bounds__(128) k_sarl_scan(Dims d, State s, risvec_param
     const float lam = (float)p.rate;
     const size_t sV = (size_t)E * V, s2V = 2 * sV;
     const float* ac = a.action + (size_t)min(e, E - 1) * 2 * V + min(v, V - 1);
-    float na0 = 0.f, na1 = 0.f, ng2 = 0.f;
-    int narr = 0;
-    auto fetch = [&](int t) {
-        if (t < T) {
-            na0 = __ldg(ac + (size_t)t * s2V);
-            na1 = __ldg(ac + (size_t)t * s2V + V);
-            ng2 = __ldg(a.g2 + (size_t)t * sV + ev);
-            narr = a.arrivals != nullptr ? __ldg(a.arrivals + (size_t)t * sV + ev) : 0;
-        }
+    // inputs are fetched four steps ahead through a small register ring (the loads of steps
+    // t+4..t+7 are in flight while steps t..t+3 compute), plus an L2 prefetch 32 steps ahead
+    constexpr int D = 4;
+    float ra0[D], ra1[D], rg2[D];
+    int rarr[D];
+    auto fetch = [&](int slot, int t) {
+        const int tc = min(t, T - 1);
+        ra0[slot] = __ldg(ac + (size_t)tc * s2V);
+        ra1[slot] = __ldg(ac + (size_t)tc * s2V + V);
+        rg2[slot] = __ldg(a.g2 + (size_t)tc * sV + ev);
+        rarr[slot] = a.arrivals != nullptr ? __ldg(a.arrivals + (size_t)tc * sV + ev) : 0;
     };
-    fetch(0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) fetch(k, k);
     float o_rate = 0.f, o_dt = 0.f, o_dp = 0.f, o_overp = 0.f, o_overd = 0.f, o_rew = 0.f;
     int o_arr = 0;
-    for (int t = 0; t < T; ++t) {
-        const float a0 = na0, a1 = na1, g2 = ng2;
-        int arr = narr;
-        fetch(t + 1);
+    for (int tb = 0; tb < T; tb += D) {
+        float ca0[D], ca1[D], cg2[D];
+        int carr[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) { ca0[k] = ra0[k]; ca1[k] = ra1[k]; cg2[k] = rg2[k]; carr[k] = rarr[k]; }
+#pragma unroll
+        for (int k = 0; k < D; ++k) fetch(k, tb + D + k);
+        if (tb + 32 < T && (threadIdx.x & 7) == 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.g2 + (size_t)(tb + 32) * sV + ev));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ac + (size_t)(tb + 32) * s2V));
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+        const int t = tb + k;
+        if (t >= T) break;
+        const float a0 = ca0[k], a1 = ca1[k], g2 = cg2[k];
+        int arr = carr[k];
         if (act && a.arrivals == nullptr) arr = draw_arrival(d, e, v, step0 + t, lam);
         const float rate = log1p_sfu(__fmul_rn(a0, __fmul_rn(coef, g2)));  // natural log, SARL:159
         const float data_t = __fmul_rn(rate, c_dt);
@@ -641,6 +790,7 @@ __global__ void __launch_bounds__(128) k_sarl_scan(Dims d, State s, risvec_param
             if (v == 0 && a.out.reward != nullptr) a.out.reward[(size_t)t * E + e] = rew;
         }
         o_rate = rate; o_dt = data_t; o_dp = data_p; o_overp = overp; o_overd = overd; o_rew = rew; o_arr = arr;
+        }
     }
     if (act && T > 0) {
         s.databuf[ev] = buf;

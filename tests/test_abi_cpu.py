@@ -70,3 +70,30 @@ def test_no_cpu_fallback_without_gpu(lib):
     lib.risvec_default_params(0, C.byref(p))
     h = C.c_void_p()
     assert lib.risvec_create(C.byref(p), 0, 4, 8, 40, 3, 0, 1, 0, C.byref(h)) == -4  # RISVEC_ERR_NODEVICE
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package (python or CUDA)
+    may import, include or execute it, and the package has no CPU implementation to fall back to."""
+    pkg = os.path.join(ROOT, "ris_vec_marl_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "env_oracle" in text:
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+
+
+def test_header_and_ctypes_agree_on_record_sizes(lib):
+    src = open(os.path.join(ROOT, "include", "risvec.h")).read()
+    get = lambda name: int(re.search(rf"#define {name} (\d+)", src).group(1))
+    assert get("RISVEC_SARL_OUT_WORDS") == _lib.SARL_OUT_WORDS
+    assert get("RISVEC_MARL_IN_WORDS") == _lib.MARL_IN_WORDS
+    assert get("RISVEC_MARL_OUT_WORDS") == _lib.MARL_OUT_WORDS
+    assert get("RISVEC_ABI_VERSION") == lib.risvec_abi_version()
+    n_stat = int(re.search(r"RISVEC_NSTAT = (\d+)", src).group(1))
+    assert n_stat == _lib.NSTAT and len(_lib.STAT_COLUMNS) == 13
+    fields = re.findall(r"^\s+RISVEC_F_([A-Z_]+)", src, flags=re.M)
+    assert len([f for f in fields if f != "COUNT"]) == len(_lib.FIELDS)

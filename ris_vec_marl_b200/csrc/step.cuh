@@ -1107,6 +1107,9 @@ __global__ void __launch_bounds__(32) k_sarl_v8(Dims d, State s, risvec_params_t
 // (DataBuf, MEC queue).  The `last_*` statistics are produced only for the final step of the
 // launch (they are state, not a per-step trace, in this kernel); launches that ask for the
 // `stats` / `last_power` traces use the shape-generic k_marl_rollout.
+#ifndef RISVEC_MARL_U
+#define RISVEC_MARL_U 4  // steps per software-pipeline group of k_marl_v8 (2: 0.145 ms, 3-6: 0.115 ms, 8: 0.118 ms)
+#endif
 struct MarlIn {
     float a0, a1;
     int arr;
@@ -1305,28 +1308,33 @@ __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t
         }
     };
 
-    // software pipeline over pairs: inputs of pair p+2 are requested, pair p+1 runs its
-    // state-independent part, pair p runs the queue recursion
-    MarlIn c0, c1, n0, n1, m0, m1;
-    MarlHeavy h0, h1, g0, g1;
-    const unsigned P = (T > 0) ? (unsigned)(T - 1) >> 1 : 0;  // full pairs before the last 1-2 steps
-    load_in(c0, 0); load_in(c1, 1);
-    load_in(n0, 2); load_in(n1, 3);
-    heavy(c0, h0); heavy(c1, h1);
+    // software pipeline over groups of U steps: inputs of group q+2 are requested, group q+1 runs
+    // its state-independent part, group q runs the queue recursion.  The last step of the
+    // launch is always scanned outside the loop (it also produces the `last_*` state).
+    constexpr int U = RISVEC_MARL_U;
+    MarlIn c[U], n[U], m[U];
+    MarlHeavy h[U], hn[U];
+    const unsigned NQ = (T > 0) ? (unsigned)(T - 1) / U : 0;  // full groups strictly before the last step
+#pragma unroll
+    for (int u = 0; u < U; ++u) { load_in(c[u], u); load_in(n[u], U + u); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) heavy(c[u], h[u]);
     unsigned t = 0;
-    for (unsigned pr = 0; pr < P; ++pr, t += 2) {
-        load_in(m0, t + 4); load_in(m1, t + 5);
-        heavy(n0, g0); heavy(n1, g1);
-        scan_step(c0, h0, t, No{});
-        scan_step(c1, h1, t + 1, No{});
-        c0 = n0; c1 = n1; n0 = m0; n1 = m1; h0 = g0; h1 = g1;
+    for (unsigned q = 0; q < NQ; ++q, t += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) load_in(m[u], t + 2 * U + u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) heavy(n[u], hn[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) scan_step(c[u], h[u], t + u, No{});
+#pragma unroll
+        for (int u = 0; u < U; ++u) { c[u] = n[u]; n[u] = m[u]; h[u] = hn[u]; }
     }
-    if (T > 0) {
-        if (t + 1 < (unsigned)T) {  // two steps left
-            scan_step(c0, h0, t, No{});
-            scan_step(c1, h1, t + 1, Yes{});
-        } else {
-            scan_step(c0, h0, t, Yes{});
+    if (T > 0) {  // 1..U steps left; (c, h) hold them
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (t + u + 1 < (unsigned)T) scan_step(c[u], h[u], t + u, No{});
+            else if (t + u + 1 == (unsigned)T) scan_step(c[u], h[u], t + u, Yes{});
         }
     }
 

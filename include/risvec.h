@@ -98,6 +98,17 @@ enum risvec_field {
     RISVEC_F_STATS,          /* f32 [E,RISVEC_NSTAT] last_* scalars of the last step     */
     RISVEC_F_LAST_POWER,     /* f32 [E,2,V] last_power_W                                 */
     RISVEC_F_STEP_CTR,       /* i64 [E]    steps taken (keys the on-device RNG)          */
+    /* NOMA pairing stage of the MARL driver (risvec_pair_noma) */
+    RISVEC_F_PAIR_HIST,      /* f32 [E,V*V] pair_affinity_hist (marl_train_bcd.py:1288)  */
+    RISVEC_F_PAIR_STREAK,    /* i32 [E,V]  unpaired_streak (:1290)                       */
+    RISVEC_F_PAIR_TAU,       /* f64 [E]    last_tau_now (:1341)                          */
+    RISVEC_F_PAIR_K,         /* i32 [E]    last_K_now (:1342)                            */
+    RISVEC_F_PAIR_MASK,      /* u8  [E,V*V] last_mask_mat, 1 = selectable (:1337-1340)   */
+    RISVEC_F_PAIR_ROUNDS,    /* i32 [E]    back-off rounds used by the last solve (:1493)*/
+    RISVEC_F_NOMA_PARTNER,   /* i32 [E,V]  noma_groups, partner encoding (rollout input) */
+    RISVEC_F_NOMA_NGROUPS,   /* i32 [E]    len(noma_groups); 0 = no groups yet           */
+    RISVEC_F_NOMA_PAIRS,     /* i32 [E,V]  pairs (i0,j0,i1,j1,...) in list order, -1 pad */
+    RISVEC_F_NOMA_NPAIRS,    /* i32 [E]    len(pairs)                                    */
     RISVEC_F_COUNT
 };
 
@@ -240,6 +251,46 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
  * action [E,2,V] and phase [E,M] radians. */
 int risvec_observe(risvec_env_t* env, float* obs, void* stream);
 int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float* phase, void* stream);
+
+/* ---- NOMA pairing: the stage that builds `noma_groups` for Environ.step ----
+ * Knobs of the pairing pipeline; defaults = Config.__init__ and the getattr fall-backs at the call
+ * site (marl_train_bcd.py:435-441,489-503,1404-1418,1481-1498); yaml != 0 applies the overlay of
+ * the shipped config.yaml (:639-660,716-732). */
+typedef struct risvec_pairing {
+    int32_t min_pair_target;     /* :489,1413  (max(1, .) is applied by the library) */
+    int32_t mwm_backoff_rounds;  /* :440,1493 */
+    int32_t relax_topk_step;     /* :1482 */
+    int32_t qos_enable;          /* :1427 */
+    double mwm_accept_quantile, mwm_accept_q_step;      /* :439,441 */
+    double completion_min_quantile;                     /* :282,300 */
+    double relax_tau_factor_per_round, tau_back_floor_db; /* :1483,1498 */
+    double score_w_delta_db, score_w_history;           /* :1416-1417 */
+    double abs_gain_min_db;                             /* :1418 (-inf = off) */
+    double qos_soft_penalty_dbscore;                    /* :1449 */
+    double pair_hist_decay;                             /* :1404 */
+} risvec_pairing_t;
+
+#define RISVEC_PAIR_MAX_V 12 /* the matching is an exact DP over 2^V vehicle subsets (:360-393) */
+
+int risvec_default_pairing(int n_veh, int yaml, risvec_pairing_t* out);
+
+/* One driver step of the pairing stage for every env (marl_train_bcd.py:1315-1344,1404-1406,
+ * 1413-1524,1542-1561): [decay != 0: pair_affinity_hist *= pair_hist_decay]; [recalc_mask != 0:
+ * tau = quantile_{tau_q}(|dg_dB| strong x weak), mask from tau and row top-`topk` -> PAIR_TAU,
+ * PAIR_K, PAIR_MASK; else the solve runs on the all-ones mask as the reference does]; QoS soft mask
+ * from `p01` (offload power in [0,1], row 0 of the env action: pass `action` with
+ * p01_env_stride = 2V) and the env's noise_power / P_max / R_min_bpsHz; score matrix; exact
+ * max-weight matching on the edges above the (1 - accept_q) quantile; greedy completion; back-off
+ * rounds; then noma_groups -> NOMA_PARTNER / NOMA_NGROUPS (feed them to risvec_rollout_marl),
+ * NOMA_PAIRS / NOMA_NPAIRS, and the history / streak updates.  reuse [E] i32 (device, may be
+ * NULL): != 0 keeps that env's frozen groups (:1542-1547) and only updates history / streak.
+ * V <= RISVEC_PAIR_MAX_V.  Results are exact (same pairs as the reference) up to float64 ulp
+ * differences of log10 / log2 at non-structural near-ties; at exact ties numpy's argsort order is
+ * taken as stable (lower index first). */
+int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float* p01, int64_t p01_env_stride,
+                     int topk, double tau_q, int recalc_mask, const int32_t* reuse, int decay, void* stream);
+/* start of an episode (:1282-1297): history, streak, thresholds, mask and frozen groups cleared */
+int risvec_pair_reset(risvec_env_t* env, void* stream);
 
 /* Episode statistics for the multi-GPU reduction: sums over this shard's E envs of the
  * RISVEC_F_STATS columns and of RISVEC_F_REWARD, written (accumulate = 0) or added (accumulate != 0)

@@ -200,3 +200,110 @@ def apply_marl_yaml_params(env, params=None):
     env.bandwidth_hz = env.bandwidth * 1e6
     env.noise_power = env.N0_W_per_Hz * env.bandwidth_hz  # marl_train_bcd.py:589-590
     return env
+
+
+# ---------------------------------------------------------------------------------------------
+# NOMA pairing stage of the MARL driver (module-level code of `marl_train_bcd.py`)
+# ---------------------------------------------------------------------------------------------
+PAIRING_HELPERS = ("_anneal_topk", "_build_feasible_mask_from_delta_g", "_score_matrix_from_gain_and_history",
+                   "_relax_mask_once", "_mwm_completion", "_mwm_primary", "_adaptive_threshold_from_delta_g",
+                   "_qos_pair_feasible")
+
+
+class _StableArgsortNumpy:
+    """numpy with `argsort` forced to `kind='stable'` (see the header of oracle/pairing_oracle.py: at
+    exact ties the default kind depends on the SIMD kernel numpy picks for the host CPU)."""
+
+    def __getattr__(self, name):
+        return getattr(_np, name)
+
+    @staticmethod
+    def argsort(a, axis=-1, kind=None, order=None):
+        return _np.argsort(a, axis=axis, kind="stable", order=order)
+
+
+class PairingReference:
+    """The reference's pairing helpers and the driver's own call-site statements, compiled from the
+    unmodified `Simulation-MARL-BCD/marl_train_bcd.py` source (selected by AST, nothing is copied).
+
+    `helpers[name]` are the module-level functions; `step(...)` executes, in one persistent namespace,
+    the statements the driver runs per step: the mask block (`if config.mask_enable:` holding
+    `need_recalc`) and everything from `gamma_decay = ...` to the `unpaired_streak` update."""
+
+    def __init__(self, n_veh: int, config_overrides: dict | None = None, stable_argsort: bool = True):
+        import ast
+        import math
+        import types
+        import typing
+
+        path = os.path.join(REFERENCE_ROOT, "Simulation-MARL-BCD", "marl_train_bcd.py")
+        src = open(path, "r", encoding="utf-8").read()
+        tree = ast.parse(src)
+        npx = _StableArgsortNumpy() if stable_argsort else _np
+        cfg = types.SimpleNamespace(
+            n_veh=n_veh, mask_enable=True, mask_topk_start=n_veh - 1, mask_topk_end=max(4, n_veh // 2),
+            mask_tau_q_start=0.2, mask_tau_q_end=0.4, mask_warmup_episodes=200,
+            min_pair_target=max(1, n_veh // 4), use_mwm_primary=True, mwm_allow_singles=True,
+            mwm_accept_quantile=0.10, mwm_backoff_rounds=5, mwm_accept_q_step=0.05, qos_enable=True,
+            qos_R_min_bpsHz=0.15, pairing_threshold_quantile=0.5)
+        for k, v in (config_overrides or {}).items():
+            setattr(cfg, k, v)
+        self.config = cfg
+        ns = {"np": npx, "math": math, "random": _pyrandom, "config": cfg, "Optional": typing.Optional,
+              "Set": typing.Set, "Tuple": typing.Tuple, "List": typing.List, "__name__": "ref_pairing"}
+        # the *last* definition of each name wins, as at import time in the driver
+        fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in PAIRING_HELPERS]
+        exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+        self.helpers = {n: ns[n] for n in PAIRING_HELPERS}
+
+        loop = None
+        for node in ast.walk(tree):
+            if isinstance(node, ast.For) and isinstance(node.target, ast.Name) and node.target.id == "i_step":
+                seg = ast.get_source_segment(src, node) or ""
+                if "pair_affinity_hist" in seg and "mwm_backoff_rounds" in seg:
+                    loop = node
+                    break
+        if loop is None:
+            raise RuntimeError("pairing call site not found in " + path)
+        segs = [(ast.get_source_segment(src, s) or "") for s in loop.body]
+        i_mask = next(i for i, t in enumerate(segs) if t.startswith("if config.mask_enable") and "need_recalc" in t)
+        i_lo = next(i for i, t in enumerate(segs) if t.startswith("gamma_decay"))
+        i_hi = next(i for i, t in enumerate(segs) if t.startswith("for u in range(config.n_veh)")
+                    and "unpaired_streak" in t)
+        self._mask_code = compile(ast.Module(body=[loop.body[i_mask]], type_ignores=[]), path, "exec")
+        self._pair_code = compile(ast.Module(body=loop.body[i_lo:i_hi + 1], type_ignores=[]), path, "exec")
+        import torch
+        ns.update(torch=torch, agents=[types.SimpleNamespace(policy=types.SimpleNamespace(device="cpu"))],
+                  K_STEPS_FOR_RIS_OPTIMIZATION=100)
+        self.ns = ns
+        self.new_episode(0)
+
+    def new_episode(self, i_episode: int):
+        """Per-episode initialisation the driver does at `marl_train_bcd.py:1282-1300`."""
+        n = self.config.n_veh
+        self.ns.update(
+            i_episode=int(i_episode), last_mask_mat=None, last_tau_now=None, last_K_now=None, last_q_now=None,
+            last_feasible_mask_gpu=None, pair_affinity_hist=_np.zeros((n, n), dtype=_np.float32),
+            prev_pairs=set(), unpaired_streak=_np.zeros((n,), dtype=_np.int32),
+            freeze_group_in_episode=True, freeze_recalc_every=0, freeze_unstick_prob=0.0,
+            freeze_reward_drop_ratio=0.05, episode_groups=None, last_env_global=None, ep_env_best=-1e18,
+            unstick_used_flag=False, ep_mask_zero_ratio_sum=0.0)
+
+    def step(self, i_step: int, gains, p01, env_noise_power: float, env_P_max: float, freeze: bool = True):
+        import contextlib
+        import io
+        import types
+
+        ns = self.ns
+        ns.update(i_step=int(i_step), current_channel_gains=_np.asarray(gains, dtype=float),
+                  offload_power_for_pairing=_np.asarray(p01, dtype=float), freeze_group_in_episode=bool(freeze),
+                  env=types.SimpleNamespace(noise_power=float(env_noise_power), P_max=float(env_P_max)),
+                  feasible_mask_gpu=None, mask_mat=None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            exec(self._mask_code, ns)
+            exec(self._pair_code, ns)
+        return dict(pairs=[(int(a), int(b)) for a, b in ns["pairs"]],
+                    groups=[[int(u) for u in g] for g in ns["noma_groups"]],
+                    hist=_np.array(ns["pair_affinity_hist"]), streak=_np.array(ns["unpaired_streak"]),
+                    mask=None if ns["mask_mat"] is None else _np.array(ns["mask_mat"]).astype(_np.uint8),
+                    tau=ns["last_tau_now"], K=ns["last_K_now"], rounds=int(ns["round_id"]))

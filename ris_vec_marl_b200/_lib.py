@@ -15,7 +15,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("RISVEC_LIB") or os.path.join(PKG_DIR, "librisvec.so")  # override: A/B builds
 SOURCES = ["risvec.cu"]
-HEADERS = ["common.cuh", "geom.cuh", "ris.cuh", "step.cuh"]
+HEADERS = ["common.cuh", "geom.cuh", "ris.cuh", "step.cuh", "pairing.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 
@@ -41,7 +41,10 @@ STAT_COLUMNS = ("delay_mean", "energy_mean", "delay_local_mean", "delay_edge_q_m
 
 FIELDS = ("pos_x", "pos_y", "dir", "vel", "dist", "angle", "amp", "theta_re", "theta_im", "phase_real", "gains",
           "DataBuf", "data_t", "data_p", "over_data", "over_power", "vehicle_rate", "data_r", "reward_user",
-          "reward", "mec_queue_cycles", "stats", "last_power_W", "step_ctr")
+          "reward", "mec_queue_cycles", "stats", "last_power_W", "step_ctr",
+          "pair_hist", "unpaired_streak", "pair_tau", "pair_k", "pair_mask", "pair_rounds",
+          "noma_partner", "noma_ngroups", "noma_pairs", "noma_npairs")
+PAIR_MAX_V = 12
 
 
 class RisvecLibraryError(RuntimeError):
@@ -74,6 +77,20 @@ class Params(C.Structure):
         ("fc_GHz", C.c_double), ("shadow_std_los", C.c_double), ("shadow_std_nlos", C.c_double),
         ("rician_K_dB", C.c_double), ("veh_ant_gain", C.c_double),
         ("t_factor1", C.c_double), ("t_factor2", C.c_double), ("penalty1", C.c_double), ("penalty2", C.c_double),
+    ]
+
+
+class Pairing(C.Structure):
+    """Mirror of `risvec_pairing_t` (knobs of the NOMA pairing stage, marl_train_bcd.py:435-441,1404-1498)."""
+
+    _fields_ = [
+        ("min_pair_target", C.c_int32), ("mwm_backoff_rounds", C.c_int32), ("relax_topk_step", C.c_int32),
+        ("qos_enable", C.c_int32),
+        ("mwm_accept_quantile", C.c_double), ("mwm_accept_q_step", C.c_double),
+        ("completion_min_quantile", C.c_double),
+        ("relax_tau_factor_per_round", C.c_double), ("tau_back_floor_db", C.c_double),
+        ("score_w_delta_db", C.c_double), ("score_w_history", C.c_double), ("abs_gain_min_db", C.c_double),
+        ("qos_soft_penalty_dbscore", C.c_double), ("pair_hist_decay", C.c_double),
     ]
 
 
@@ -120,6 +137,10 @@ EXPORTS = {
                                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_map_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "risvec_default_pairing": (C.c_int, [C.c_int, C.c_int, C.POINTER(Pairing)]),
+    "risvec_pair_noma": (C.c_int, [C.c_void_p, C.POINTER(Pairing), C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int,
+                                   C.c_void_p, C.c_int, C.c_void_p]),
+    "risvec_pair_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
     "risvec_shard_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "risvec_launch_count": (C.c_int64, [C.c_void_p]),
 }

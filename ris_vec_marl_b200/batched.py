@@ -13,9 +13,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CHANNEL, FIELDS, NSTAT, STAT_COLUMNS, VARIANT, MarlOut, Params, SarlOut, check
+from ._lib import CHANNEL, FIELDS, NSTAT, STAT_COLUMNS, VARIANT, MarlOut, Pairing, Params, SarlOut, check
 
 _PARAM_NAMES = {n for n, _ in Params._fields_} - {"_pad0"}
+_PAIRING_NAMES = {n for n, _ in Pairing._fields_}
 _LANE_FIELDS = ("up_lanes", "down_lanes", "left_lanes", "right_lanes")
 MARL_TRACES = ("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate", "over_power", "stats", "last_power")
 SARL_TRACES = ("reward", "DataBuf", "data_t", "data_p", "over_power", "over_data", "rate")
@@ -33,6 +34,24 @@ def default_params(variant: str) -> Params:
     p = Params()
     check(_lib.load_library().risvec_default_params(VARIANT[variant], C.byref(p)))
     return p
+
+
+def default_pairing(n_veh: int, yaml: bool = False) -> Pairing:
+    p = Pairing()
+    check(_lib.load_library().risvec_default_pairing(int(n_veh), int(bool(yaml)), C.byref(p)))
+    return p
+
+
+def mask_schedule(i_episode: int, n_veh: int, topk_start=None, topk_end=None, tau_q_start=0.2, tau_q_end=0.4,
+                  warmup_episodes=200):
+    """(K_now, q_now) of the driver's mask curriculum (`_anneal_topk` marl_train_bcd.py:128-132 and
+    :1323-1332).  Defaults are `Config.__init__` (:499-503); config.yaml uses 7, 7, 0.10, 0.25."""
+    k_start = n_veh - 1 if topk_start is None else topk_start
+    k_end = max(4, n_veh // 2) if topk_end is None else topk_end
+    i = max(0, min(i_episode, warmup_episodes))
+    k = round(k_end + (k_start - k_end) * (1.0 - i / max(1, warmup_episodes)))
+    prog = min(1.0, i_episode / max(1, warmup_episodes))
+    return int(min(max(k, 1), n_veh - 1)), float(tau_q_start + (tau_q_end - tau_q_start) * prog)
 
 
 def marl_yaml_overrides() -> dict:
@@ -84,11 +103,15 @@ class BatchedEnviron:
             ptr, rows, cols, eb, fl = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int()
             check(self._lib.risvec_field(self._h, i, C.byref(ptr), C.byref(rows), C.byref(cols), C.byref(eb),
                                          C.byref(fl)))
-            typestr = ("<f" if fl.value else "<i") + str(eb.value)
-            per_env_scalar = name in ("reward", "mec_queue_cycles", "step_ctr")
+            typestr = "|u1" if eb.value == 1 else ("<f" if fl.value else "<i") + str(eb.value)
+            per_env_scalar = name in ("reward", "mec_queue_cycles", "step_ctr", "pair_tau", "pair_k", "pair_rounds",
+                                      "noma_ngroups", "noma_npairs")
             shape = (rows.value,) if per_env_scalar else (rows.value, cols.value)
             self._views[name] = torch.as_tensor(_DevView(ptr.value, shape, typestr), device=self.device)
         self._views["last_power_W"] = self._views["last_power_W"].view(self.E, 2, self.V)
+        for name in ("pair_hist", "pair_mask"):
+            self._views[name] = self._views[name].view(self.E, self.V, self.V)
+        self.pairing = default_pairing(self.V)
 
     # ------------------------------------------------------------------ params
     def _set_lanes(self, name, vals):
@@ -354,6 +377,38 @@ class BatchedEnviron:
         """{name: tensor [E]} of the reference's `last_*` attributes after the latest step."""
         st = self._views["stats"]
         return {n: st[:, i] for i, n in enumerate(STAT_COLUMNS)}
+
+    # ------------------------------------------------------------------ NOMA pairing (driver stage)
+    def set_pairing(self, yaml=False, **kw):
+        """Pairing knobs (`risvec_pairing_t`); `yaml=True` starts from the shipped config.yaml overlay."""
+        if yaml:
+            self.pairing = default_pairing(self.V, yaml=True)
+        for k, v in kw.items():
+            if k not in _PAIRING_NAMES:
+                raise AttributeError(f"unknown pairing parameter {k!r}")
+            setattr(self.pairing, k, type(getattr(self.pairing, k))(v))
+
+    def pair_reset(self):
+        """Start of an episode (marl_train_bcd.py:1282-1297)."""
+        check(self._lib.risvec_pair_reset(self._h, self.stream))
+
+    def pair_noma(self, p01, topk, tau_q, recalc_mask=True, reuse=None, decay=True):
+        """One driver step of the pairing stage (marl_train_bcd.py:1315-1561) for every env.
+
+        `p01`: offload power in [0,1], either [E,V] or the env action [E,2,V] (row 0 is used).
+        `topk`, `tau_q`: K_now / q_now of the mask curriculum (`mask_schedule`).  Returns the
+        zero-copy views `(noma_partner [E,V], noma_ngroups [E])` to hand to `rollout_marl`."""
+        t = self._dev(p01, torch.float32)
+        if tuple(t.shape) == (self.E, 2, self.V):
+            stride = 2 * self.V
+        elif tuple(t.shape) == (self.E, self.V):
+            stride = self.V
+        else:
+            raise ValueError(f"p01 must be [E,V] or [E,2,V], got {tuple(t.shape)}")
+        ru = self._dev(reuse, torch.int32, (self.E,))
+        check(self._lib.risvec_pair_noma(self._h, C.byref(self.pairing), self._p(t), stride, int(topk), float(tau_q),
+                                         int(bool(recalc_mask)), self._p(ru), int(bool(decay)), self.stream))
+        return self._views["noma_partner"], self._views["noma_ngroups"]
 
     def shard_stats(self, out=None, accumulate=False):
         """f64 [NSTAT + 1] sums over this shard's envs (stats columns, then global reward);

@@ -1,0 +1,424 @@
+// Batched NOMA pairing: the stage the MARL driver runs before every Environ.step to build
+// `noma_groups` (Simulation-MARL-BCD/marl_train_bcd.py:1315-1561 and the helpers at :128-398,
+// :842-881).  One warp per env; every decision is warp-uniform, the N x N matrices and the 2^N
+// matching table live in that warp's slice of shared memory.  All score arithmetic is float64
+// with explicit round-to-nearest intrinsics in the reference's operation order (thresholds are
+// order statistics of the very values they are compared with, so exact ties are structural and
+// must survive); pair_affinity_hist is float32 as in the reference (:1288).
+#pragma once
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace risvec {
+
+struct PairArgs {
+    const float* p01;        // [E, *] offload power in [0,1] (row 0 of the env action), env stride below
+    long long p01_stride;
+    const int* reuse;        // [E] or NULL: != 0 -> frozen groups (:1542-1547), solve skipped
+    int topk;                // K_now (:1324)
+    double tau_q;            // q_now (:1329)
+    int recalc, decay;
+    int min_pairs, backoff_rounds;
+    double accept_q, accept_q_step, completion_q;
+    int relax_topk_step;
+    double relax_tau_factor, tau_floor;
+    double w_delta, abs_min_db, qos_pen;
+    float w_hist, decay_f;
+    int qos_enable;
+    double noise, P_max, R_min;
+    // state (arena fields RISVEC_F_PAIR_* / RISVEC_F_NOMA_*)
+    float* hist;
+    int* streak;
+    double* tau;
+    int* lastk;
+    int* partner;
+    int* ngroups;
+    int* pairs;
+    int* npairs;
+    int* rounds;
+    unsigned char* mask;
+};
+
+__host__ __device__ inline size_t pair_smem_bytes(int N) {
+    const size_t NN = (size_t)N * N, NS = (size_t)1 << N;
+    size_t b = 8 * (4 * (size_t)N + 2 * NN + NS + 2);   // gl, pw, g15, g12 | S, W | dp | slot
+    b += 4 * (NN + (size_t)N + 2);                      // Hs (f32) | pr (int)
+    b += NS + 4 * NN + (size_t)N;                       // ch | feas, qos, tmp, valid | wk
+    return (b + 15) / 16 * 16;
+}
+
+struct PairCtx {
+    int N, NN, NS, lane;
+    double *gl, *pw, *g15, *g12, *S, *W, *dp, *slot;
+    float* Hs;
+    int* pr;
+    signed char* ch;
+    unsigned char *feas, *qos, *tmp, *valid, *wk;
+
+    __device__ void carve(unsigned char* base, int n, int ln) {
+        N = n; NN = n * n; NS = 1 << n; lane = ln;
+        gl = (double*)base; pw = gl + N; g15 = pw + N; g12 = g15 + N;
+        S = g12 + N; W = S + NN; dp = W + NN; slot = dp + NS;
+        Hs = (float*)(slot + 2);
+        pr = (int*)(Hs + NN);
+        ch = (signed char*)(pr + N + 2);
+        feas = (unsigned char*)(ch + NS); qos = feas + NN; tmp = qos + NN; valid = tmp + NN; wk = valid + NN;
+    }
+
+    static __device__ __forceinline__ int wsum(int v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        return v;
+    }
+
+    // numpy.quantile(vals[valid], q, method="linear") incl. numpy's two-sided _lerp; n -> count
+    __device__ double quantile(const double* vals, double q, int& n) {
+        int c = 0;
+        for (int e = lane; e < NN; e += 32) c += valid[e] ? 1 : 0;
+        n = wsum(c);
+        if (n == 0) return 0.0;
+        const double vi = __dmul_rn((double)(n - 1), q);
+        int lo, hi;
+        double t = 0.0;
+        if (vi >= (double)(n - 1)) lo = hi = n - 1;
+        else if (vi < 0.0) lo = hi = 0;
+        else { const double f = floor(vi); lo = (int)f; hi = lo + 1; t = __dsub_rn(vi, f); }
+        for (int e = lane; e < NN; e += 32) {
+            if (!valid[e]) continue;
+            const double v = vals[e];
+            int r = 0;
+            for (int o = 0; o < NN; ++o) {
+                const double u = vals[o];
+                r += (valid[o] && (u < v || (u == v && o < e))) ? 1 : 0;
+            }
+            if (r == lo) slot[0] = v;
+            if (r == hi) slot[1] = v;
+        }
+        __syncwarp();
+        const double a = slot[0], b = slot[1];
+        __syncwarp();
+        const double dlt = __dsub_rn(b, a);
+        double r = __dadd_rn(a, __dmul_rn(dlt, t));
+        if (t >= 0.5) r = __dsub_rn(b, __dmul_rn(dlt, __dsub_rn(1.0, t)));
+        return r;
+    }
+
+    // _adaptive_threshold_from_delta_g (:842-855)
+    __device__ double adaptive_tau(double q) {
+        if (N < 2) return 0.0;
+        if (lane < N) {
+            int r = 0;
+            const double v = g15[lane];
+            for (int o = 0; o < N; ++o) r += (g15[o] < v || (g15[o] == v && o < lane)) ? 1 : 0;
+            wk[lane] = r < N / 2;
+        }
+        __syncwarp();
+        for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
+            valid[e] = (!wk[i]) && wk[j];
+            W[e] = fabs(__dsub_rn(g15[i], g15[j]));
+        }
+        __syncwarp();
+        int n;
+        const double tau = quantile(W, q, n);
+        return n ? tau : 0.0;
+    }
+
+    // _build_feasible_mask_from_delta_g (:134-156) -> feas
+    __device__ void build_mask(double tau, int K) {
+        for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
+            tmp[e] = (i != j) && !(fabs(__dsub_rn(g15[i], g15[j])) < tau);
+        }
+        __syncwarp();
+        for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
+            unsigned char keep = tmp[e];
+            if (keep) {
+                const double dme = fabs(__dsub_rn(g15[i], g15[j]));
+                int cnt = 0, r = 0;
+                for (int o = 0; o < N; ++o) {
+                    if (!tmp[i * N + o]) continue;
+                    ++cnt;
+                    const double du = fabs(__dsub_rn(g15[i], g15[o]));
+                    r += (du > dme || (du == dme && o < j)) ? 1 : 0;
+                }
+                if (cnt > K && r >= K) keep = 0;
+            }
+            qos[e] = keep;      // scratch (the QoS mask is built later)
+        }
+        __syncwarp();
+        for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
+            feas[e] = qos[e] & qos[j * N + i];
+        }
+        __syncwarp();
+    }
+
+    // call-site loop :1428-1440 over _qos_pair_feasible (:858-881) -> qos
+    __device__ void build_qos(const PairArgs& a) {
+        const double nz = __dadd_rn(a.noise, 1e-12);
+        for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
+            unsigned char ok = 0;
+            if (i != j) {
+                const double pi = __dmul_rn(pw[i], a.P_max), pj = __dmul_rn(pw[j], a.P_max);
+                const double gi = gl[i], gj = gl[j];
+                double g_near, g_far, p_near, p_far;
+                if (gi >= gj) { g_near = gi; g_far = gj; p_near = pi; p_far = pj; }
+                else { g_near = gj; g_far = gi; p_near = pj; p_far = pi; }
+                const double den = __dadd_rn(__dadd_rn(__dmul_rn(p_near, g_far), a.noise), 1e-12);
+                const double sf = __ddiv_rn(__dmul_rn(p_far, g_far), den);
+                const double sn = __ddiv_rn(__dmul_rn(p_near, g_near), nz);
+                const double rf = log2(__dadd_rn(1.0, fmax(0.0, sf)));
+                const double rn = log2(__dadd_rn(1.0, fmax(0.0, sn)));
+                ok = (rf >= a.R_min) && (rn >= a.R_min);
+            }
+            qos[e] = ok;
+        }
+        __syncwarp();
+    }
+
+    // _score_matrix_from_gain_and_history (:164-194) -> S
+    __device__ void score(const PairArgs& a) {
+        const double ninf = -CUDART_INF;
+        bool any = false;
+        for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
+            const double d12 = fabs(__dsub_rn(g12[i], g12[j]));
+            const bool ok = (g12[i] >= a.abs_min_db) || (g12[j] >= a.abs_min_db);
+            S[e] = __dadd_rn(__dmul_rn(a.w_delta, d12), (double)__fmul_rn(a.w_hist, Hs[e]));
+            tmp[e] = ok;
+            any |= (feas[e] > 0) && ok;
+        }
+        any = __any_sync(kFull, any);
+        __syncwarp();
+        for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
+            const bool keep = (feas[e] > 0) && (any ? (tmp[e] != 0) : true);
+            double v = keep ? S[e] : ninf;
+            if (a.qos_enable && qos[e] == 0 && isfinite(v)) v = __dsub_rn(v, a.qos_pen);
+            if (i == j) v = ninf;
+            S[e] = v;
+        }
+        __syncwarp();
+    }
+
+    // _relax_mask_once (:260-275): feas |= (delta >= tau_db, off-diagonal) | row top-k by delta
+    __device__ void relax(double tau_db, int topk) {
+        const int k = min(topk, N - 1);
+        for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
+            const double dme = fabs(__dsub_rn(g12[i], g12[j]));
+            bool on = feas[e] > 0 || ((dme >= tau_db) && i != j);
+            if (!on && topk >= 1) {
+                int r = 0;
+                for (int o = 0; o < N; ++o) {
+                    const double du = fabs(__dsub_rn(g12[i], g12[o]));
+                    r += (du > dme || (du == dme && o < j)) ? 1 : 0;
+                }
+                on = r < k;
+            }
+            tmp[e] = on;
+        }
+        __syncwarp();
+        for (int e = lane; e < NN; e += 32) feas[e] = tmp[e];
+        __syncwarp();
+    }
+
+    // _mwm_primary (:326-398), allow_singles = True.  Returns the number of pairs written to pr.
+    __device__ int mwm_primary(double accept_q) {
+        const double ninf = -CUDART_INF;
+        for (int e = lane; e < NN; e += 32) valid[e] = isfinite(S[e]);
+        __syncwarp();
+        int n;
+        const double q = fmin(fmax(accept_q, 0.0), 1.0);
+        const double thr = quantile(S, __dsub_rn(1.0, q), n);
+        if (n == 0) return 0;
+        for (int e = lane; e < NN; e += 32) W[e] = (valid[e] && S[e] >= thr) ? S[e] : ninf;
+        const int full = NS - 1;
+        if (lane == 0) { dp[full] = 0.0; ch[full] = -1; }
+        for (int level = N - 1; level >= 0; --level) {
+            __syncwarp();
+            for (int m = lane; m < full; m += 32) {
+                if (__popc(m) != level) continue;
+                const int i = __ffs(~m) - 1;
+                const int bi = 1 << i;
+                double bw = ninf;
+                int c = -1;
+                const double w1 = dp[m | bi];
+                if (w1 > bw) { bw = w1; c = -1; }
+                for (int j = i + 1; j < N; ++j) {
+                    if (m & (1 << j)) continue;
+                    const double we = W[i * N + j];
+                    if (!isfinite(we)) continue;
+                    const double w2 = dp[m | bi | (1 << j)];
+                    const double sum = __dadd_rn(we, w2);
+                    if (isfinite(w2) && sum > bw) { bw = sum; c = j; }
+                }
+                dp[m] = bw;
+                ch[m] = (signed char)c;
+            }
+        }
+        __syncwarp();
+        int np = 0;
+        if (lane == 0) {
+            int m = 0;
+            while (m != full) {
+                const int i = __ffs(~m) - 1;
+                const int c = ch[m];
+                if (c >= 0) { pr[2 * np] = i; pr[2 * np + 1] = c; ++np; m |= (1 << i) | (1 << c); }
+                else m |= 1 << i;
+            }
+        }
+        np = __shfl_sync(kFull, np, 0);
+        __syncwarp();
+        return np;
+    }
+
+    // _mwm_completion (:276-324): greedy top-up, candidates ordered by (S, i, j) descending
+    __device__ int completion(int np, int min_pairs, double cq) {
+        for (int e = lane; e < NN; e += 32) valid[e] = isfinite(S[e]);
+        __syncwarp();
+        int n;
+        const double thr = quantile(S, cq, n);
+        if (n == 0) return np;
+        unsigned occ = 0;
+        for (int k = 0; k < 2 * np; ++k) occ |= 1u << pr[k];
+        while (np < min_pairs) {
+            double bv = -CUDART_INF;
+            int be = -1;
+            for (int e = lane; e < NN; e += 32) {
+                const int i = e / N, j = e - i * N;
+                if (i >= j || !valid[e] || !(S[e] >= thr)) continue;
+                if ((occ >> i & 1u) || (occ >> j & 1u)) continue;
+                if (be < 0 || S[e] > bv || (S[e] == bv && e > be)) { bv = S[e]; be = e; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(kFull, bv, o);
+                const int oe = __shfl_xor_sync(kFull, be, o);
+                if (oe >= 0 && (be < 0 || ov > bv || (ov == bv && oe > be))) { bv = ov; be = oe; }
+            }
+            if (be < 0) break;
+            const int i = be / N, j = be - i * N;
+            if (lane == 0) { pr[2 * np] = i; pr[2 * np + 1] = j; }
+            occ |= (1u << i) | (1u << j);
+            ++np;
+        }
+        __syncwarp();
+        return np;
+    }
+};
+
+__global__ void k_pair_noma(Dims d, State s, PairArgs a) {
+    extern __shared__ __align__(16) unsigned char pair_smem[];
+    const int N = d.V, NN = N * N;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const long long e = (long long)blockIdx.x * wpc + wib;
+    if (e >= d.E) return;    // whole warps leave together; only __syncwarp is used below
+    PairCtx c;
+    c.carve(pair_smem + pair_smem_bytes(N) * wib, N, lane);
+
+    float* H = a.hist + e * NN;
+    for (int x = lane; x < NN; x += 32) {
+        const float h = H[x];
+        c.Hs[x] = a.decay ? __fmul_rn(h, a.decay_f) : h;     // :1406 (float32 array *= python float)
+    }
+    if (lane < N) {
+        const double g = s.gains[e * N + lane];
+        c.gl[lane] = g;
+        c.pw[lane] = (double)a.p01[e * a.p01_stride + lane];
+        c.g15[lane] = __dmul_rn(10.0, log10(fmax(g, 1e-15)));
+        c.g12[lane] = __dmul_rn(10.0, log10(fmax(g, 1e-12)));
+    }
+    __syncwarp();
+
+    double tau;
+    int K;
+    if (a.recalc) {                                           // :1319-1343
+        tau = c.adaptive_tau(a.tau_q);
+        K = a.topk;
+        c.build_mask(tau, K);
+        for (int x = lane; x < NN; x += 32) a.mask[e * NN + x] = c.feas[x];
+        if (lane == 0) { a.tau[e] = tau; a.lastk[e] = K; }
+    } else {                                                  // :1421-1424 (mask_mat is None on these steps)
+        tau = a.tau[e];
+        K = a.lastk[e];
+        for (int x = lane; x < NN; x += 32) { const int i = x / N; c.feas[x] = (x - i * N) != i; }
+        __syncwarp();
+    }
+
+    int np = 0, rounds = 0;
+    const bool frozen = a.reuse != nullptr && a.reuse[e] != 0 && a.ngroups[e] > 0;
+    if (frozen) {                                             // :1542-1547
+        np = a.npairs[e];
+        if (lane < 2 * np) c.pr[lane] = a.pairs[e * N + lane];
+        __syncwarp();
+    } else {
+        if (a.qos_enable) c.build_qos(a);
+        c.score(a);                                           // :1441-1450
+        double accept_q = a.accept_q;
+        np = c.mwm_primary(accept_q);                         // :1456-1461
+        if (np < a.min_pairs) np = c.completion(np, a.min_pairs, a.completion_q);   // :1464-1465
+        int K_back = K;
+        double tau_back = tau;
+        while (np < a.min_pairs && rounds < a.backoff_rounds) {     // :1493-1524
+            ++rounds;
+            K_back = min(N - 1, K_back + a.relax_topk_step);
+            tau_back = fmax(a.tau_floor, __dmul_rn(tau_back, a.relax_tau_factor));
+            c.relax(tau_back, K_back);
+            c.score(a);
+            accept_q = fmax(0.05, __dsub_rn(accept_q, a.accept_q_step));
+            np = c.mwm_primary(accept_q);
+            if (np < a.min_pairs) np = c.completion(np, a.min_pairs, a.completion_q);
+        }
+        __syncwarp();
+        // groups = pairs + singles (:1550-1553) in the partner / ngroups encoding of the rollout
+        unsigned used = 0;
+        for (int k = 0; k < 2 * np; ++k) used |= 1u << c.pr[k];
+        if (lane < N) {
+            int p = RISVEC_PARTNER_SINGLE;
+            for (int k = 0; k < np; ++k) {
+                if (c.pr[2 * k] == lane) p = c.pr[2 * k + 1];
+                if (c.pr[2 * k + 1] == lane) p = c.pr[2 * k] | RISVEC_PARTNER_SECOND;
+            }
+            a.partner[e * N + lane] = p;
+        }
+        if (lane < N) a.pairs[e * N + lane] = lane < 2 * np ? c.pr[lane] : -1;
+        if (lane == 0) {
+            a.npairs[e] = np;
+            a.ngroups[e] = np + (N - __popc(used));
+        }
+    }
+    if (lane == 0) a.rounds[e] = rounds;
+
+    // history / streak updates (:1556-1561)
+    unsigned used = 0;
+    for (int k = 0; k < 2 * np; ++k) used |= 1u << c.pr[k];
+    if (lane < np) {
+        const int i = c.pr[2 * lane], j = c.pr[2 * lane + 1];
+        c.Hs[i * N + j] = __fadd_rn(c.Hs[i * N + j], 1.0f);
+        c.Hs[j * N + i] = __fadd_rn(c.Hs[j * N + i], 1.0f);
+    }
+    __syncwarp();
+    for (int x = lane; x < NN; x += 32) H[x] = c.Hs[x];
+    if (lane < N) {
+        int* sk = a.streak + e * N + lane;
+        *sk = (used >> lane & 1u) ? 0 : *sk + 1;
+    }
+}
+
+// new episode (:1282-1297): history, streak, thresholds and frozen groups cleared
+__global__ void k_pair_reset(Dims d, PairArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = d.V, NN = N * N;
+    if (t >= (long long)d.E * NN) return;
+    a.hist[t] = 0.f;
+    a.mask[t] = 0;
+    if (t < (long long)d.E * N) { a.streak[t] = 0; a.partner[t] = RISVEC_PARTNER_NONE; a.pairs[t] = -1; }
+    if (t < d.E) { a.tau[t] = 0.0; a.lastk[t] = 0; a.ngroups[t] = 0; a.npairs[t] = 0; a.rounds[t] = 0; }
+}
+
+}  // namespace risvec

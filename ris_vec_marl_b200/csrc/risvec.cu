@@ -10,6 +10,7 @@
 #include "geom.cuh"
 #include "ris.cuh"
 #include "step.cuh"
+#include "pairing.cuh"
 
 using namespace risvec;
 
@@ -323,7 +324,11 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
         {RISVEC_F_OVER_POWER, E, V, 4, 1}, {RISVEC_F_RATE, E, V, 4, 1}, {RISVEC_F_DATA_R, E, V, 4, 0},
         {RISVEC_F_REWARD_USER, E, V, 4, 1}, {RISVEC_F_REWARD, E, 1, 4, 1}, {RISVEC_F_MECQ, E, 1, 8, 1},
         {RISVEC_F_STATS, E, RISVEC_NSTAT, 4, 1}, {RISVEC_F_LAST_POWER, E, 2 * V, 4, 1},
-        {RISVEC_F_STEP_CTR, E, 1, 8, 0}};
+        {RISVEC_F_STEP_CTR, E, 1, 8, 0},
+        {RISVEC_F_PAIR_HIST, E, V * V, 4, 1}, {RISVEC_F_PAIR_STREAK, E, V, 4, 0}, {RISVEC_F_PAIR_TAU, E, 1, 8, 1},
+        {RISVEC_F_PAIR_K, E, 1, 4, 0}, {RISVEC_F_PAIR_MASK, E, V * V, 1, 0}, {RISVEC_F_PAIR_ROUNDS, E, 1, 4, 0},
+        {RISVEC_F_NOMA_PARTNER, E, V, 4, 0}, {RISVEC_F_NOMA_NGROUPS, E, 1, 4, 0}, {RISVEC_F_NOMA_PAIRS, E, V, 4, 0},
+        {RISVEC_F_NOMA_NPAIRS, E, 1, 4, 0}};
     size_t off = 0;
     for (int i = 0; i < RISVEC_F_COUNT; ++i) {
         const Spec& sp = specs[i];
@@ -839,6 +844,74 @@ int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float
     const long long n = (long long)d.E * (2 * d.V + d.M);
     k_map_actions_sarl<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, raw, action, phase);
     return check_launch(env, "k_map_actions_sarl");
+}
+
+int risvec_default_pairing(int n_veh, int yaml, risvec_pairing_t* out) {
+    if (!out) return fail(RISVEC_ERR_INVALID, "out is NULL");
+    if (n_veh < 1) return fail(RISVEC_ERR_INVALID, "n_veh must be >= 1");
+    memset(out, 0, sizeof(*out));
+    out->min_pair_target = n_veh / 4 > 1 ? n_veh / 4 : 1;
+    out->mwm_backoff_rounds = 5; out->relax_topk_step = 1; out->qos_enable = 1;
+    out->mwm_accept_quantile = 0.10; out->mwm_accept_q_step = 0.05; out->completion_min_quantile = 0.30;
+    out->relax_tau_factor_per_round = 0.95; out->tau_back_floor_db = 3.0;
+    out->score_w_delta_db = 1.0; out->score_w_history = 0.3; out->abs_gain_min_db = -INFINITY;
+    out->qos_soft_penalty_dbscore = 6.0; out->pair_hist_decay = 0.97;
+    if (yaml) {  // config.yaml: min_pair_target 3, mwm_backoff_rounds 3, abs_gain_min_db -120
+        out->min_pair_target = 3; out->mwm_backoff_rounds = 3; out->abs_gain_min_db = -120.0;
+    }
+    return RISVEC_OK;
+}
+
+static PairArgs pair_state_args(risvec_env* env) {
+    auto P = [&](int f) { return (void*)(env->arena + env->fields[f].offset); };
+    PairArgs a;
+    memset(&a, 0, sizeof(a));
+    a.hist = (float*)P(RISVEC_F_PAIR_HIST); a.streak = (int*)P(RISVEC_F_PAIR_STREAK);
+    a.tau = (double*)P(RISVEC_F_PAIR_TAU); a.lastk = (int*)P(RISVEC_F_PAIR_K);
+    a.mask = (unsigned char*)P(RISVEC_F_PAIR_MASK); a.rounds = (int*)P(RISVEC_F_PAIR_ROUNDS);
+    a.partner = (int*)P(RISVEC_F_NOMA_PARTNER); a.ngroups = (int*)P(RISVEC_F_NOMA_NGROUPS);
+    a.pairs = (int*)P(RISVEC_F_NOMA_PAIRS); a.npairs = (int*)P(RISVEC_F_NOMA_NPAIRS);
+    return a;
+}
+
+int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float* p01, int64_t p01_env_stride,
+                     int topk, double tau_q, int recalc_mask, const int32_t* reuse, int decay, void* stream) {
+    if (!env || !cfg || !p01) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    const int V = env->dims.V;
+    if (V > RISVEC_PAIR_MAX_V)
+        return fail(RISVEC_ERR_UNSUPPORTED, "pairing is an exact matching over 2^V subsets: V = %d > %d", V,
+                    RISVEC_PAIR_MAX_V);
+    if (p01_env_stride < V) return fail(RISVEC_ERR_INVALID, "p01_env_stride %lld < V", (long long)p01_env_stride);
+    if (!(tau_q >= 0.0 && tau_q <= 1.0)) return fail(RISVEC_ERR_INVALID, "tau_q must be in [0, 1]");
+    CUDA_TRY(cudaSetDevice(env->device));
+    PairArgs a = pair_state_args(env);
+    a.p01 = p01; a.p01_stride = p01_env_stride; a.reuse = reuse;
+    a.topk = topk; a.tau_q = tau_q; a.recalc = recalc_mask != 0; a.decay = decay != 0;
+    a.min_pairs = cfg->min_pair_target > 1 ? cfg->min_pair_target : 1;
+    a.backoff_rounds = cfg->mwm_backoff_rounds;
+    a.accept_q = cfg->mwm_accept_quantile; a.accept_q_step = cfg->mwm_accept_q_step;
+    a.completion_q = cfg->completion_min_quantile;
+    a.relax_topk_step = cfg->relax_topk_step;
+    a.relax_tau_factor = cfg->relax_tau_factor_per_round; a.tau_floor = cfg->tau_back_floor_db;
+    a.w_delta = cfg->score_w_delta_db; a.abs_min_db = cfg->abs_gain_min_db; a.qos_pen = cfg->qos_soft_penalty_dbscore;
+    a.w_hist = (float)cfg->score_w_history; a.decay_f = (float)cfg->pair_hist_decay;
+    a.qos_enable = cfg->qos_enable != 0;
+    a.noise = env->params.noise_power; a.P_max = env->params.P_max; a.R_min = env->params.R_min_bpsHz;
+    const size_t per = pair_smem_bytes(V);
+    const int wpc = V <= 8 ? 4 : (V <= 10 ? 2 : 1);
+    const int blocks = (env->dims.E + wpc - 1) / wpc;
+    k_pair_noma<<<blocks, 32 * wpc, per * wpc, (cudaStream_t)stream>>>(env->dims, env->st, a);
+    return check_launch(env, "k_pair_noma");
+}
+
+int risvec_pair_reset(risvec_env_t* env, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(env->device));
+    PairArgs a = pair_state_args(env);
+    const long long n = (long long)env->dims.E * env->dims.V * env->dims.V;
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    k_pair_reset<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, a);
+    return check_launch(env, "k_pair_reset");
 }
 
 int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream) {

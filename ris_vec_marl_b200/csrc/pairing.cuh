@@ -26,7 +26,7 @@ struct PairArgs {
     double w_delta, abs_min_db, qos_pen;
     float w_hist, decay_f;
     int qos_enable;
-    double noise, P_max, R_min;
+    double noise, P_max, sinr_min;   // sinr_min: see build_qos
     // state (arena fields RISVEC_F_PAIR_* / RISVEC_F_NOMA_*)
     float* hist;
     int* streak;
@@ -48,16 +48,18 @@ __host__ __device__ inline size_t pair_smem_bytes(int N) {
     return (b + 15) / 16 * 16;
 }
 
+template <int N>
 struct PairCtx {
-    int N, NN, NS, lane;
+    static constexpr int NN = N * N, NS = 1 << N;
+    int lane;
     double *gl, *pw, *g15, *g12, *S, *W, *dp, *slot;
     float* Hs;
     int* pr;
     signed char* ch;
     unsigned char *feas, *qos, *tmp, *valid, *wk;
 
-    __device__ void carve(unsigned char* base, int n, int ln) {
-        N = n; NN = n * n; NS = 1 << n; lane = ln;
+    __device__ void carve(unsigned char* base, int ln) {
+        lane = ln;
         gl = (double*)base; pw = gl + N; g15 = pw + N; g12 = g15 + N;
         S = g12 + N; W = S + NN; dp = W + NN; slot = dp + NS;
         Hs = (float*)(slot + 2);
@@ -72,7 +74,8 @@ struct PairCtx {
         return v;
     }
 
-    // numpy.quantile(vals[valid], q, method="linear") incl. numpy's two-sided _lerp; n -> count
+    // numpy.quantile(vals[valid], q, method="linear") incl. numpy's two-sided _lerp; n -> count.
+    // `vals` must hold +inf wherever `valid` is 0 (so invalid entries never rank below a valid one).
     __device__ double quantile(const double* vals, double q, int& n) {
         int c = 0;
         for (int e = lane; e < NN; e += 32) c += valid[e] ? 1 : 0;
@@ -84,24 +87,37 @@ struct PairCtx {
         if (vi >= (double)(n - 1)) lo = hi = n - 1;
         else if (vi < 0.0) lo = hi = 0;
         else { const double f = floor(vi); lo = (int)f; hi = lo + 1; t = __dsub_rn(vi, f); }
-        for (int e = lane; e < NN; e += 32) {
-            if (!valid[e]) continue;
-            const double v = vals[e];
-            int r = 0;
-            for (int o = 0; o < NN; ++o) {
-                const double u = vals[o];
-                r += (valid[o] && (u < v || (u == v && o < e))) ? 1 : 0;
+        constexpr int EPL = (NN + 31) / 32;     // entries per lane
+        double v[EPL];
+        int r[EPL];
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int e = lane + 32 * k;
+            v[k] = e < NN ? vals[e] : CUDART_INF;
+            r[k] = 0;
+        }
+        // rank = #(u < v) + #(u == v, o < e): "<=" below the own index, "<" above it
+#pragma unroll 8
+        for (int o = 0; o < NN; ++o) {
+            const double u = vals[o];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) r[k] += (o < lane + 32 * k) ? (u <= v[k]) : (u < v[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int e = lane + 32 * k;
+            if (e < NN && valid[e]) {
+                if (r[k] == lo) slot[0] = v[k];
+                if (r[k] == hi) slot[1] = v[k];
             }
-            if (r == lo) slot[0] = v;
-            if (r == hi) slot[1] = v;
         }
         __syncwarp();
         const double a = slot[0], b = slot[1];
         __syncwarp();
         const double dlt = __dsub_rn(b, a);
-        double r = __dadd_rn(a, __dmul_rn(dlt, t));
-        if (t >= 0.5) r = __dsub_rn(b, __dmul_rn(dlt, __dsub_rn(1.0, t)));
-        return r;
+        double res = __dadd_rn(a, __dmul_rn(dlt, t));
+        if (t >= 0.5) res = __dsub_rn(b, __dmul_rn(dlt, __dsub_rn(1.0, t)));
+        return res;
     }
 
     // _adaptive_threshold_from_delta_g (:842-855)
@@ -116,8 +132,9 @@ struct PairCtx {
         __syncwarp();
         for (int e = lane; e < NN; e += 32) {
             const int i = e / N, j = e - i * N;
-            valid[e] = (!wk[i]) && wk[j];
-            W[e] = fabs(__dsub_rn(g15[i], g15[j]));
+            const bool ok = (!wk[i]) && wk[j];
+            valid[e] = ok;
+            W[e] = ok ? fabs(__dsub_rn(g15[i], g15[j])) : CUDART_INF;
         }
         __syncwarp();
         int n;
@@ -171,9 +188,9 @@ struct PairCtx {
                 const double den = __dadd_rn(__dadd_rn(__dmul_rn(p_near, g_far), a.noise), 1e-12);
                 const double sf = __ddiv_rn(__dmul_rn(p_far, g_far), den);
                 const double sn = __ddiv_rn(__dmul_rn(p_near, g_near), nz);
-                const double rf = log2(__dadd_rn(1.0, fmax(0.0, sf)));
-                const double rn = log2(__dadd_rn(1.0, fmax(0.0, sn)));
-                ok = (rf >= a.R_min) && (rn >= a.R_min);
+                // log2(1 + max(0, sinr)) >= R_min  <=>  max(0, sinr) >= a.sinr_min, the smallest double
+                // for which the host libm evaluates the left side true (log2(1 + x) is monotone)
+                ok = (fmax(0.0, sf) >= a.sinr_min) && (fmax(0.0, sn) >= a.sinr_min);
             }
             qos[e] = ok;
         }
@@ -227,35 +244,45 @@ struct PairCtx {
         __syncwarp();
     }
 
+    // S with +inf in place of the non-edges -> W (the layout `quantile` wants); valid = edge
+    __device__ void stage_edges() {
+        for (int e = lane; e < NN; e += 32) {
+            const bool ok = isfinite(S[e]);
+            valid[e] = ok;
+            W[e] = ok ? S[e] : CUDART_INF;
+        }
+        __syncwarp();
+    }
+
     // _mwm_primary (:326-398), allow_singles = True.  Returns the number of pairs written to pr.
+    // dp(mask) always expands the lowest unused vehicle i, so the table is filled by "lowest unset
+    // bit" levels i = N-1 .. 0: level i holds the 2^(N-1-i) masks (ones below i, zero at i, any bits
+    // above) and depends only on levels > i.  Values and option order (single first, then j
+    // ascending, strict >) are those of the reference's memoised recursion.  A non-edge carries
+    // W = -inf, and -inf + dp never beats the single option, which is the reference's `continue`.
     __device__ int mwm_primary(double accept_q) {
         const double ninf = -CUDART_INF;
-        for (int e = lane; e < NN; e += 32) valid[e] = isfinite(S[e]);
-        __syncwarp();
+        stage_edges();
         int n;
         const double q = fmin(fmax(accept_q, 0.0), 1.0);
-        const double thr = quantile(S, __dsub_rn(1.0, q), n);
+        const double thr = quantile(W, __dsub_rn(1.0, q), n);
         if (n == 0) return 0;
         for (int e = lane; e < NN; e += 32) W[e] = (valid[e] && S[e] >= thr) ? S[e] : ninf;
-        const int full = NS - 1;
+        constexpr int full = NS - 1;
         if (lane == 0) { dp[full] = 0.0; ch[full] = -1; }
-        for (int level = N - 1; level >= 0; --level) {
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
             __syncwarp();
-            for (int m = lane; m < full; m += 32) {
-                if (__popc(m) != level) continue;
-                const int i = __ffs(~m) - 1;
-                const int bi = 1 << i;
-                double bw = ninf;
+            const int low = (1 << i) - 1, cnt = 1 << (N - 1 - i);
+            for (int k = lane; k < cnt; k += 32) {
+                const int m = low | (k << (i + 1));
+                const int mi = m | (1 << i);
+                double bw = dp[mi];             // option 1: i stays single (always finite)
                 int c = -1;
-                const double w1 = dp[m | bi];
-                if (w1 > bw) { bw = w1; c = -1; }
+#pragma unroll
                 for (int j = i + 1; j < N; ++j) {
-                    if (m & (1 << j)) continue;
-                    const double we = W[i * N + j];
-                    if (!isfinite(we)) continue;
-                    const double w2 = dp[m | bi | (1 << j)];
-                    const double sum = __dadd_rn(we, w2);
-                    if (isfinite(w2) && sum > bw) { bw = sum; c = j; }
+                    const double sum = __dadd_rn(W[i * N + j], dp[mi | (1 << j)]);
+                    if (!(m >> j & 1) && sum > bw) { bw = sum; c = j; }
                 }
                 dp[m] = bw;
                 ch[m] = (signed char)c;
@@ -279,10 +306,9 @@ struct PairCtx {
 
     // _mwm_completion (:276-324): greedy top-up, candidates ordered by (S, i, j) descending
     __device__ int completion(int np, int min_pairs, double cq) {
-        for (int e = lane; e < NN; e += 32) valid[e] = isfinite(S[e]);
-        __syncwarp();
+        stage_edges();
         int n;
-        const double thr = quantile(S, cq, n);
+        const double thr = quantile(W, cq, n);
         if (n == 0) return np;
         unsigned occ = 0;
         for (int k = 0; k < 2 * np; ++k) occ |= 1u << pr[k];
@@ -312,14 +338,15 @@ struct PairCtx {
     }
 };
 
+template <int N>
 __global__ void k_pair_noma(Dims d, State s, PairArgs a) {
     extern __shared__ __align__(16) unsigned char pair_smem[];
-    const int N = d.V, NN = N * N;
+    constexpr int NN = N * N;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const long long e = (long long)blockIdx.x * wpc + wib;
     if (e >= d.E) return;    // whole warps leave together; only __syncwarp is used below
-    PairCtx c;
-    c.carve(pair_smem + pair_smem_bytes(N) * wib, N, lane);
+    PairCtx<N> c;
+    c.carve(pair_smem + pair_smem_bytes(N) * wib, lane);
 
     float* H = a.hist + e * NN;
     for (int x = lane; x < NN; x += 32) {

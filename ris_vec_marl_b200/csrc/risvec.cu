@@ -862,6 +862,27 @@ int risvec_default_pairing(int n_veh, int yaml, risvec_pairing_t* out) {
     return RISVEC_OK;
 }
 
+// Smallest double x >= 0 with log2(1.0 + x) >= R_min as this host's libm evaluates it (the
+// reference's test is `np.log2(1.0 + max(0.0, sinr)) >= R_min`, marl_train_bcd.py:877-881; the
+// left side is monotone in sinr).  R_min <= 0 is always satisfied.
+static double qos_sinr_threshold(double R_min) {
+    if (!(R_min > 0.0)) return -INFINITY;
+    if (!(R_min < 1000.0)) return INFINITY;
+    double lo = 0.0, hi = exp2(R_min) * 1.0000001;      // predicate false at lo, true at hi
+    while (!(log2(1.0 + hi) >= R_min)) hi *= 2.0;
+    int64_t a, b;
+    memcpy(&a, &lo, 8);
+    memcpy(&b, &hi, 8);
+    while (b - a > 1) {     // non-negative doubles are ordered like their bit patterns
+        const int64_t mid = a + (b - a) / 2;
+        double x;
+        memcpy(&x, &mid, 8);
+        if (log2(1.0 + x) >= R_min) b = mid; else a = mid;
+    }
+    memcpy(&hi, &b, 8);
+    return hi;
+}
+
 static PairArgs pair_state_args(risvec_env* env) {
     auto P = [&](int f) { return (void*)(env->arena + env->fields[f].offset); };
     PairArgs a;
@@ -896,11 +917,19 @@ int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float
     a.w_delta = cfg->score_w_delta_db; a.abs_min_db = cfg->abs_gain_min_db; a.qos_pen = cfg->qos_soft_penalty_dbscore;
     a.w_hist = (float)cfg->score_w_history; a.decay_f = (float)cfg->pair_hist_decay;
     a.qos_enable = cfg->qos_enable != 0;
-    a.noise = env->params.noise_power; a.P_max = env->params.P_max; a.R_min = env->params.R_min_bpsHz;
+    a.noise = env->params.noise_power; a.P_max = env->params.P_max;
+    a.sinr_min = qos_sinr_threshold(env->params.R_min_bpsHz);
     const size_t per = pair_smem_bytes(V);
     const int wpc = V <= 8 ? 4 : (V <= 10 ? 2 : 1);
     const int blocks = (env->dims.E + wpc - 1) / wpc;
-    k_pair_noma<<<blocks, 32 * wpc, per * wpc, (cudaStream_t)stream>>>(env->dims, env->st, a);
+    switch (V) {
+#define RISVEC_PAIR_CASE(n) \
+    case n: k_pair_noma<n><<<blocks, 32 * wpc, per * wpc, (cudaStream_t)stream>>>(env->dims, env->st, a); break;
+        RISVEC_PAIR_CASE(1) RISVEC_PAIR_CASE(2) RISVEC_PAIR_CASE(3) RISVEC_PAIR_CASE(4) RISVEC_PAIR_CASE(5)
+        RISVEC_PAIR_CASE(6) RISVEC_PAIR_CASE(7) RISVEC_PAIR_CASE(8) RISVEC_PAIR_CASE(9) RISVEC_PAIR_CASE(10)
+        RISVEC_PAIR_CASE(11) RISVEC_PAIR_CASE(12)
+#undef RISVEC_PAIR_CASE
+    }
     return check_launch(env, "k_pair_noma");
 }
 

@@ -292,6 +292,41 @@ int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float
 /* start of an episode (:1282-1297): history, streak, thresholds, mask and frozen groups cleared */
 int risvec_pair_reset(risvec_env_t* env, void* stream);
 
+/* ---- replay memory: Simulation-MARL-BCD/buffer.py, device resident ----
+ * Same seven arrays as ReplayBuffer.__init__ (buffer.py:4-14): state / new_state [mem_size,
+ * input_shape * n_agents] f32, action [mem_size, n_actions * n_agents] f32, reward_global [mem_size]
+ * f32, reward_local [mem_size, n_agents] f32, terminal [mem_size] u8 (bool), mask [mem_size,
+ * n_agents^2] f32; zero-filled at creation. */
+typedef struct risvec_replay risvec_replay_t;
+enum risvec_replay_field {
+    RISVEC_RB_STATE = 0, RISVEC_RB_ACTION, RISVEC_RB_REWARD_G, RISVEC_RB_REWARD_L, RISVEC_RB_NEW_STATE,
+    RISVEC_RB_TERMINAL, RISVEC_RB_MASK, RISVEC_RB_COUNT
+};
+int risvec_replay_create(int device, int64_t mem_size, int input_shape, int n_actions, int n_agents,
+                         risvec_replay_t** out);
+int risvec_replay_destroy(risvec_replay_t* rb);
+int risvec_replay_field(risvec_replay_t* rb, int field, void** dev_ptr, int64_t* rows, int64_t* cols, int* elem_bytes);
+int64_t risvec_replay_count(const risvec_replay_t* rb); /* mem_cntr */
+/* store_transition (buffer.py:16-25) for E transitions at once: transition e goes to slot
+ * (mem_cntr + e) % mem_size, then mem_cntr += E.  All pointers device; done [E] u8 may be NULL
+ * (then done_all applies to every row); mask_flat [E, n_agents^2] f32 may be NULL (all ones, the
+ * driver's choice when a step built no mask, marl_train_bcd.py:1786-1787). */
+int risvec_replay_store(risvec_replay_t* rb, int E, const float* state, const float* action, const float* reward_g,
+                        const float* reward_l, const float* state_, const uint8_t* done, int done_all,
+                        const float* mask_flat, void* stream);
+/* the same with the driver's assembly fused in (marl_train_bcd.py:1776-1790): action row = per agent
+ * [intent_probs[i, :] with the diagonal zeroed (:1390) | power_raw[i, 0:2]] (n_actions must be
+ * n_agents + 2); mask from the u8 RISVEC_F_PAIR_MASK layout [E, n_agents^2] (NULL: all ones). */
+int risvec_replay_store_marl(risvec_replay_t* rb, int E, const float* state, const float* intent_probs,
+                             const float* power_raw, const float* reward_g, const float* reward_l,
+                             const float* state_, const uint8_t* done, int done_all, const uint8_t* mask_u8,
+                             void* stream);
+/* sample_buffer (buffer.py:27-39) for B caller-drawn slot indices idx [B] i64 (device), each in
+ * [0, min(mem_cntr, mem_size)); outputs are [B, ...] device arrays shaped like the fields. */
+int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* states, float* actions,
+                         float* rewards_g, float* rewards_l, float* states_, uint8_t* dones, float* masks,
+                         void* stream);
+
 /* Episode statistics for the multi-GPU reduction: sums over this shard's E envs of the
  * RISVEC_F_STATS columns and of RISVEC_F_REWARD, written (accumulate = 0) or added (accumulate != 0)
  * to out [RISVEC_NSTAT + 1] f64 (device). */

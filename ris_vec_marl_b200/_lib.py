@@ -15,7 +15,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("RISVEC_LIB") or os.path.join(PKG_DIR, "librisvec.so")  # override: A/B builds
 SOURCES = ["risvec.cu"]
-HEADERS = ["common.cuh", "geom.cuh", "ris.cuh", "step.cuh", "pairing.cuh"]
+HEADERS = ["common.cuh", "geom.cuh", "ris.cuh", "step.cuh", "pairing.cuh", "replay.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 
@@ -45,6 +45,8 @@ FIELDS = ("pos_x", "pos_y", "dir", "vel", "dist", "angle", "amp", "theta_re", "t
           "pair_hist", "unpaired_streak", "pair_tau", "pair_k", "pair_mask", "pair_rounds",
           "noma_partner", "noma_ngroups", "noma_pairs", "noma_npairs")
 PAIR_MAX_V = 12
+REPLAY_FIELDS = ("state_memory", "action_memory", "reward_global_memory", "reward_local_memory", "new_state_memory",
+                 "terminal_memory", "mask_memory")
 
 
 class RisvecLibraryError(RuntimeError):
@@ -141,6 +143,14 @@ EXPORTS = {
     "risvec_pair_noma": (C.c_int, [C.c_void_p, C.POINTER(Pairing), C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int,
                                    C.c_void_p, C.c_int, C.c_void_p]),
     "risvec_pair_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "risvec_replay_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "risvec_replay_destroy": (C.c_int, [C.c_void_p]),
+    "risvec_replay_field": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "risvec_replay_count": (C.c_int64, [C.c_void_p]),
+    "risvec_replay_store": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]),
+    "risvec_replay_store_marl": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]),
+    "risvec_replay_sample": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_void_p]),
     "risvec_shard_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "risvec_launch_count": (C.c_int64, [C.c_void_p]),
 }

@@ -11,6 +11,7 @@
 #include "ris.cuh"
 #include "step.cuh"
 #include "pairing.cuh"
+#include "replay.cuh"
 
 using namespace risvec;
 
@@ -66,6 +67,15 @@ struct risvec_env {
     cudaStream_t s_in, s_out;
     cudaEvent_t ev[2 * 16 + 2];
     int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
+};
+
+struct risvec_replay {
+    ReplayMem m;
+    int device;
+    long long mem_cntr;
+    char* base;
+    size_t off[RISVEC_RB_COUNT + 1];
+    int64_t launches;
 };
 
 namespace {
@@ -941,6 +951,119 @@ int risvec_pair_reset(risvec_env_t* env, void* stream) {
     const int threads = 256, blocks = (int)((n + threads - 1) / threads);
     k_pair_reset<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, a);
     return check_launch(env, "k_pair_reset");
+}
+
+int risvec_replay_create(int device, int64_t mem_size, int input_shape, int n_actions, int n_agents,
+                         risvec_replay_t** out) {
+    if (!out) return fail(RISVEC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (mem_size < 1 || input_shape < 1 || n_actions < 1 || n_agents < 1)
+        return fail(RISVEC_ERR_INVALID, "mem_size, input_shape, n_actions, n_agents must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(RISVEC_ERR_NODEVICE, "no CUDA device visible: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(RISVEC_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    risvec_replay* rb = new (std::nothrow) risvec_replay();
+    if (!rb) return fail(RISVEC_ERR_INVALID, "out of host memory");
+    memset(rb, 0, sizeof(*rb));
+    rb->device = device;
+    ReplayMem& m = rb->m;
+    m.mem_size = mem_size; m.N = n_agents; m.S = input_shape * n_agents; m.A = n_actions * n_agents;
+    const size_t sz[RISVEC_RB_COUNT] = {(size_t)mem_size * m.S * 4, (size_t)mem_size * m.A * 4, (size_t)mem_size * 4,
+                                        (size_t)mem_size * m.N * 4, (size_t)mem_size * m.S * 4, (size_t)mem_size,
+                                        (size_t)mem_size * m.N * m.N * 4};
+    size_t off = 0;
+    for (int i = 0; i < RISVEC_RB_COUNT; ++i) { rb->off[i] = off; off = align_up(off + sz[i], 256); }
+    rb->off[RISVEC_RB_COUNT] = off;
+    cudaError_t ce = cudaMalloc((void**)&rb->base, off);
+    if (ce == cudaSuccess) ce = cudaMemset(rb->base, 0, off);
+    if (ce != cudaSuccess) {
+        if (rb->base) cudaFree(rb->base);
+        delete rb;
+        return fail(RISVEC_ERR_CUDA, "replay memory of %zu bytes: %s", off, cudaGetErrorString(ce));
+    }
+    m.state = (float*)(rb->base + rb->off[RISVEC_RB_STATE]); m.action = (float*)(rb->base + rb->off[RISVEC_RB_ACTION]);
+    m.reward_g = (float*)(rb->base + rb->off[RISVEC_RB_REWARD_G]);
+    m.reward_l = (float*)(rb->base + rb->off[RISVEC_RB_REWARD_L]);
+    m.state_ = (float*)(rb->base + rb->off[RISVEC_RB_NEW_STATE]);
+    m.terminal = (unsigned char*)(rb->base + rb->off[RISVEC_RB_TERMINAL]);
+    m.mask = (float*)(rb->base + rb->off[RISVEC_RB_MASK]);
+    *out = rb;
+    return RISVEC_OK;
+}
+
+int risvec_replay_destroy(risvec_replay_t* rb) {
+    if (!rb) return RISVEC_OK;
+    cudaSetDevice(rb->device);
+    if (rb->base) cudaFree(rb->base);
+    delete rb;
+    return RISVEC_OK;
+}
+
+int risvec_replay_field(risvec_replay_t* rb, int field, void** dev_ptr, int64_t* rows, int64_t* cols, int* elem_bytes) {
+    if (!rb) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (field < 0 || field >= RISVEC_RB_COUNT) return fail(RISVEC_ERR_INVALID, "unknown replay field %d", field);
+    const ReplayMem& m = rb->m;
+    const int64_t c[RISVEC_RB_COUNT] = {m.S, m.A, 1, m.N, m.S, 1, (int64_t)m.N * m.N};
+    if (dev_ptr) *dev_ptr = rb->base + rb->off[field];
+    if (rows) *rows = m.mem_size;
+    if (cols) *cols = c[field];
+    if (elem_bytes) *elem_bytes = field == RISVEC_RB_TERMINAL ? 1 : 4;
+    return RISVEC_OK;
+}
+
+int64_t risvec_replay_count(const risvec_replay_t* rb) { return rb ? rb->mem_cntr : 0; }
+
+static int replay_launch_done(risvec_replay* rb, const char* what, int E) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RISVEC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    rb->launches += 1;
+    rb->mem_cntr += E;
+    return RISVEC_OK;
+}
+
+int risvec_replay_store(risvec_replay_t* rb, int E, const float* state, const float* action, const float* reward_g,
+                        const float* reward_l, const float* state_, const uint8_t* done, int done_all,
+                        const float* mask_flat, void* stream) {
+    if (!rb || !state || !action || !reward_g || !reward_l || !state_) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    if (E < 1 || E > rb->m.mem_size) return fail(RISVEC_ERR_INVALID, "E = %d must be in [1, mem_size]", E);
+    CUDA_TRY(cudaSetDevice(rb->device));
+    k_replay_store<<<E, 128, 0, (cudaStream_t)stream>>>(rb->m, rb->mem_cntr, E, state, action, reward_g, reward_l, state_,
+                                                       done, done_all, mask_flat);
+    return replay_launch_done(rb, "k_replay_store", E);
+}
+
+int risvec_replay_store_marl(risvec_replay_t* rb, int E, const float* state, const float* intent_probs,
+                             const float* power_raw, const float* reward_g, const float* reward_l,
+                             const float* state_, const uint8_t* done, int done_all, const uint8_t* mask_u8,
+                             void* stream) {
+    if (!rb || !state || !intent_probs || !power_raw || !reward_g || !reward_l || !state_)
+        return fail(RISVEC_ERR_INVALID, "NULL argument");
+    if (E < 1 || E > rb->m.mem_size) return fail(RISVEC_ERR_INVALID, "E = %d must be in [1, mem_size]", E);
+    if (rb->m.A != rb->m.N * (rb->m.N + 2))
+        return fail(RISVEC_ERR_INVALID, "store_marl needs n_actions = n_agents + 2 (got %d per agent)", rb->m.A / rb->m.N);
+    CUDA_TRY(cudaSetDevice(rb->device));
+    k_replay_store_marl<<<E, 128, 0, (cudaStream_t)stream>>>(rb->m, rb->mem_cntr, E, state, intent_probs, power_raw,
+                                                            reward_g, reward_l, state_, done, done_all, mask_u8);
+    return replay_launch_done(rb, "k_replay_store_marl", E);
+}
+
+int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* states, float* actions,
+                         float* rewards_g, float* rewards_l, float* states_, uint8_t* dones, float* masks,
+                         void* stream) {
+    if (!rb || !idx || !states || !actions || !rewards_g || !rewards_l || !states_ || !dones || !masks)
+        return fail(RISVEC_ERR_INVALID, "NULL argument");
+    if (B < 1) return fail(RISVEC_ERR_INVALID, "B must be >= 1");
+    CUDA_TRY(cudaSetDevice(rb->device));
+    k_replay_sample<<<B, 128, 0, (cudaStream_t)stream>>>(rb->m, B, (const long long*)idx, states, actions, rewards_g,
+                                                        rewards_l, states_, dones, masks);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RISVEC_ERR_CUDA, "launch of k_replay_sample failed: %s", cudaGetErrorString(e));
+    rb->launches += 1;
+    return RISVEC_OK;
 }
 
 int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream) {

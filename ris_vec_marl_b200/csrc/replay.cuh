@@ -14,57 +14,99 @@ struct ReplayMem {
     unsigned char* terminal;
 };
 
-// generic rows: the arguments of buffer.py:16 for E transitions
-__global__ void k_replay_store(ReplayMem m, long long first, int E, const float* __restrict__ state,
-                               const float* __restrict__ action, const float* __restrict__ reward_g,
-                               const float* __restrict__ reward_l, const float* __restrict__ state_,
-                               const unsigned char* __restrict__ done, int done_all,
-                               const float* __restrict__ mask) {
-    const int e = blockIdx.x;
-    if (e >= E) return;
-    const long long slot = (first + e) % m.mem_size;
-    const int NN = m.N * m.N;
-    for (int c = threadIdx.x; c < m.S; c += blockDim.x) {
-        m.state[slot * m.S + c] = state[(size_t)e * m.S + c];
-        m.state_[slot * m.S + c] = state_[(size_t)e * m.S + c];
-    }
-    for (int c = threadIdx.x; c < m.A; c += blockDim.x) m.action[slot * m.A + c] = action[(size_t)e * m.A + c];
-    for (int c = threadIdx.x; c < m.N; c += blockDim.x) m.reward_l[slot * m.N + c] = reward_l[(size_t)e * m.N + c];
-    for (int c = threadIdx.x; c < NN; c += blockDim.x) m.mask[slot * NN + c] = mask ? mask[(size_t)e * NN + c] : 1.f;
-    if (threadIdx.x == 0) {
-        m.reward_g[slot] = reward_g[e];
-        m.terminal[slot] = done ? (done[e] != 0) : (done_all != 0);
-    }
-}
+// Sources of one store call.  MARL = 0: `action` / `mask_f` are the assembled rows of buffer.py:16;
+// MARL = 1: the driver's pieces (marl_train_bcd.py:1776-1790): action row = per agent [intent probs
+// (N, diagonal zeroed at :1390) | raw power (2)], mask row = float32 of the u8 feasibility mask.
+// A NULL mask stores all ones (the driver's choice when the step built no mask, :1786-1789).
+struct ReplaySrc {
+    const float *state, *state_, *action, *probs, *power, *reward_g, *reward_l, *mask_f;
+    const unsigned char *mask_u8, *done;
+    int done_all;
+};
 
-// MARL driver assembly (marl_train_bcd.py:1776-1790): action row = per agent [intent probs (N,
-// diagonal zeroed at :1390) | raw power (2)]; mask row = float32 of the u8 feasibility mask, all ones
-// when the step built no mask (:1786-1789).
-__global__ void k_replay_store_marl(ReplayMem m, long long first, int E, const float* __restrict__ state,
-                                    const float* __restrict__ probs, const float* __restrict__ power,
-                                    const float* __restrict__ reward_g, const float* __restrict__ reward_l,
-                                    const float* __restrict__ state_, const unsigned char* __restrict__ done,
-                                    int done_all, const unsigned char* __restrict__ mask) {
-    const int e = blockIdx.x;
-    if (e >= E) return;
-    const long long slot = (first + e) % m.mem_size;
+template <int VEC>
+struct RVec;
+template <>
+struct RVec<1> { using T = float; };
+template <>
+struct RVec<4> { using T = float4; };
+
+// Flat copy: the E rows of a call land in consecutive ring slots, so every field is one (at most
+// once wrapped) contiguous destination range.  A thread moves VEC consecutive floats of one field
+// of one row; VEC = 4 needs every row width to be a multiple of 4 (true at V = 8: 40, 80, 8, 64).
+template <int VEC, int MARL>
+__global__ void k_replay_store(ReplayMem m, long long first, int E, ReplaySrc src) {
+    using V4 = typename RVec<VEC>::T;
     const int N = m.N, NN = N * N, AW = N + 2;
-    for (int c = threadIdx.x; c < m.S; c += blockDim.x) {
-        m.state[slot * m.S + c] = state[(size_t)e * m.S + c];
-        m.state_[slot * m.S + c] = state_[(size_t)e * m.S + c];
-    }
-    for (int c = threadIdx.x; c < m.A; c += blockDim.x) {
-        const int i = c / AW, k = c - i * AW;
-        float v;
-        if (k < N) v = (k == i) ? 0.f : probs[((size_t)e * N + i) * N + k];
-        else v = power[((size_t)e * N + i) * 2 + (k - N)];
-        m.action[slot * m.A + c] = v;
-    }
-    for (int c = threadIdx.x; c < N; c += blockDim.x) m.reward_l[slot * N + c] = reward_l[(size_t)e * N + c];
-    for (int c = threadIdx.x; c < NN; c += blockDim.x) m.mask[slot * NN + c] = mask ? (float)mask[(size_t)e * NN + c] : 1.f;
-    if (threadIdx.x == 0) {
-        m.reward_g[slot] = reward_g[e];
-        m.terminal[slot] = done ? (done[e] != 0) : (done_all != 0);
+    const long long uS = (long long)E * (m.S / VEC), uA = (long long)E * (m.A / VEC), uN = (long long)E * (N / VEC),
+                    uM = (long long)E * (NN / VEC);
+    const long long total = 2 * uS + uA + uN + uM + E;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        long long u = t;
+        if (u < 2 * uS) {                                   // state, new_state
+            const bool second = u >= uS;
+            if (second) u -= uS;
+            const int w = m.S / VEC;
+            const long long e = u / w;
+            const int c = (int)(u - e * w);
+            const long long slot = (first + e) % m.mem_size;
+            const V4 v = ((const V4*)((second ? src.state_ : src.state) + e * m.S))[c];
+            ((V4*)((second ? m.state_ : m.state) + slot * m.S))[c] = v;
+            continue;
+        }
+        u -= 2 * uS;
+        if (u < uA) {                                       // action
+            const int w = m.A / VEC;
+            const long long e = u / w;
+            const int c = (int)(u - e * w);
+            const long long slot = (first + e) % m.mem_size;
+            float o[VEC];
+            if (MARL) {
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) {
+                    const int col = c * VEC + x, i = col / AW, k = col - i * AW;
+                    o[x] = k < N ? (k == i ? 0.f : src.probs[(e * N + i) * N + k]) : src.power[(e * N + i) * 2 + (k - N)];
+                }
+            } else {
+                const V4 v = ((const V4*)(src.action + e * m.A))[c];
+                memcpy(o, &v, sizeof(v));
+            }
+            V4 v;
+            memcpy(&v, o, sizeof(v));
+            ((V4*)(m.action + slot * m.A))[c] = v;
+            continue;
+        }
+        u -= uA;
+        if (u < uN) {                                       // reward_local
+            const int w = N / VEC;
+            const long long e = u / w;
+            const int c = (int)(u - e * w);
+            const long long slot = (first + e) % m.mem_size;
+            ((V4*)(m.reward_l + slot * N))[c] = ((const V4*)(src.reward_l + e * N))[c];
+            continue;
+        }
+        u -= uN;
+        if (u < uM) {                                       // mask
+            const int w = NN / VEC;
+            const long long e = u / w;
+            const int c = (int)(u - e * w);
+            const long long slot = (first + e) % m.mem_size;
+            float o[VEC];
+#pragma unroll
+            for (int x = 0; x < VEC; ++x) {
+                const long long at = e * NN + c * VEC + x;
+                o[x] = MARL ? (src.mask_u8 ? (float)src.mask_u8[at] : 1.f) : (src.mask_f ? src.mask_f[at] : 1.f);
+            }
+            V4 v;
+            memcpy(&v, o, sizeof(v));
+            ((V4*)(m.mask + slot * NN))[c] = v;
+            continue;
+        }
+        u -= uM;                                            // reward_global, terminal
+        const long long slot = (first + u) % m.mem_size;
+        m.reward_g[slot] = src.reward_g[u];
+        m.terminal[slot] = src.done ? (src.done[u] != 0) : (src.done_all != 0);
     }
 }
 

@@ -1017,9 +1017,22 @@ int risvec_replay_field(risvec_replay_t* rb, int field, void** dev_ptr, int64_t*
 
 int64_t risvec_replay_count(const risvec_replay_t* rb) { return rb ? rb->mem_cntr : 0; }
 
-static int replay_launch_done(risvec_replay* rb, const char* what, int E) {
+static int replay_store(risvec_replay* rb, int E, const ReplaySrc& src, int marl, cudaStream_t st) {
+    const ReplayMem& m = rb->m;
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };   // float4 path needs aligned sources
+    const bool vec4 = m.S % 4 == 0 && m.A % 4 == 0 && m.N % 4 == 0 && al16(src.state) && al16(src.state_) &&
+                      al16(src.action) && al16(src.reward_l);
+    const int vec = vec4 ? 4 : 1;
+    const long long total = (long long)E * ((2 * m.S + m.A + m.N + m.N * m.N) / vec + 1);
+    const int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    if (blocks > 148 * 64) blocks = 148 * 64;   // grid-stride beyond 64 blocks per SM
+    if (vec4 && marl) k_replay_store<4, 1><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);
+    else if (vec4) k_replay_store<4, 0><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);
+    else if (marl) k_replay_store<1, 1><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);
+    else k_replay_store<1, 0><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(RISVEC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(RISVEC_ERR_CUDA, "launch of k_replay_store failed: %s", cudaGetErrorString(e));
     rb->launches += 1;
     rb->mem_cntr += E;
     return RISVEC_OK;
@@ -1031,9 +1044,11 @@ int risvec_replay_store(risvec_replay_t* rb, int E, const float* state, const fl
     if (!rb || !state || !action || !reward_g || !reward_l || !state_) return fail(RISVEC_ERR_INVALID, "NULL argument");
     if (E < 1 || E > rb->m.mem_size) return fail(RISVEC_ERR_INVALID, "E = %d must be in [1, mem_size]", E);
     CUDA_TRY(cudaSetDevice(rb->device));
-    k_replay_store<<<E, 128, 0, (cudaStream_t)stream>>>(rb->m, rb->mem_cntr, E, state, action, reward_g, reward_l, state_,
-                                                       done, done_all, mask_flat);
-    return replay_launch_done(rb, "k_replay_store", E);
+    ReplaySrc src;
+    memset(&src, 0, sizeof(src));
+    src.state = state; src.state_ = state_; src.action = action; src.reward_g = reward_g; src.reward_l = reward_l;
+    src.mask_f = mask_flat; src.done = done; src.done_all = done_all;
+    return replay_store(rb, E, src, 0, (cudaStream_t)stream);
 }
 
 int risvec_replay_store_marl(risvec_replay_t* rb, int E, const float* state, const float* intent_probs,
@@ -1046,9 +1061,11 @@ int risvec_replay_store_marl(risvec_replay_t* rb, int E, const float* state, con
     if (rb->m.A != rb->m.N * (rb->m.N + 2))
         return fail(RISVEC_ERR_INVALID, "store_marl needs n_actions = n_agents + 2 (got %d per agent)", rb->m.A / rb->m.N);
     CUDA_TRY(cudaSetDevice(rb->device));
-    k_replay_store_marl<<<E, 128, 0, (cudaStream_t)stream>>>(rb->m, rb->mem_cntr, E, state, intent_probs, power_raw,
-                                                            reward_g, reward_l, state_, done, done_all, mask_u8);
-    return replay_launch_done(rb, "k_replay_store_marl", E);
+    ReplaySrc src;
+    memset(&src, 0, sizeof(src));
+    src.state = state; src.state_ = state_; src.probs = intent_probs; src.power = power_raw; src.reward_g = reward_g;
+    src.reward_l = reward_l; src.mask_u8 = mask_u8; src.done = done; src.done_all = done_all;
+    return replay_store(rb, E, src, 1, (cudaStream_t)stream);
 }
 
 int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* states, float* actions,

@@ -3,7 +3,12 @@
 observe -> V per-agent policy MLPs in torch (5 -> 512 -> LN -> 256 -> LN -> 2, tanh; the power head
 of Simulation-MARL-BCD/sac_agent.py:23-34) -> map_actions -> Environ.step (T = 1 launch).
 Random-init weights, no learner update.  Reports env-steps/s eager and replayed as a CUDA graph
-(the launch-bound regime the fused T-step rollout of bench.py avoids)."""
+(the launch-bound regime the fused T-step rollout of bench.py avoids).
+
+`--driver` adds the rest of the driver's per-step device work (marl_train_bcd.py:1304-1799): the NOMA
+pairing stage (mask + solve on the first step of each 100-step episode, frozen groups afterwards), an
+intent head (softmax over the V partners, masked by the feasibility mask), the second observation and
+the replay-memory write of the assembled transition."""
 import argparse
 import json
 import os
@@ -14,7 +19,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from ris_vec_marl_b200 import BatchedEnviron, encode_groups, marl_yaml_overrides  # noqa: E402
+from ris_vec_marl_b200 import (BatchedEnviron, ReplayBuffer, encode_groups, marl_yaml_overrides,  # noqa: E402
+                               mask_schedule)
 
 
 class Actors(torch.nn.Module):
@@ -28,13 +34,20 @@ class Actors(torch.nn.Module):
         self.b1 = torch.nn.Parameter(torch.zeros(V, 1, 512, device=dev))
         self.b2 = torch.nn.Parameter(torch.zeros(V, 1, 256, device=dev))
         self.b3 = torch.nn.Parameter(torch.zeros(V, 1, 2, device=dev))
+        self.w4 = mk(256, V)      # intent head (sac_agent.py: logits over partners)
 
     @torch.no_grad()
     def forward(self, obs):  # obs [E, V, 5] -> raw actions [E, V, 2] in (-1, 1)
         x = obs.transpose(0, 1)
         x = torch.relu(torch.nn.functional.layer_norm(torch.baddbmm(self.b1, x, self.w1), (512,)))
         x = torch.relu(torch.nn.functional.layer_norm(torch.baddbmm(self.b2, x, self.w2), (256,)))
+        self.hidden = x
         return torch.tanh(torch.baddbmm(self.b3, x, self.w3)).transpose(0, 1).contiguous()
+
+    @torch.no_grad()
+    def intent(self, mask):  # mask [E, V, V] u8 -> probs [E, V, V]
+        logits = torch.bmm(self.hidden, self.w4).transpose(0, 1).float()
+        return torch.softmax(logits.masked_fill(mask == 0, -1e9), dim=-1)
 
 
 def main():
@@ -42,6 +55,8 @@ def main():
     ap.add_argument("--envs", type=int, default=8192)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--actor-dtype", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--driver", action="store_true", help="pairing + intent head + replay write in the loop")
+    ap.add_argument("--replay-size", type=int, default=1_000_000)
     a = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = a.actor_dtype == "tf32"
     dev = torch.device("cuda", 0)
@@ -56,7 +71,34 @@ def main():
         actors = actors.to(torch.bfloat16)
     obs = torch.empty(E, V, 5, device=dev)
 
+    obs2 = torch.empty(E, V, 5, device=dev)
+    if a.driver:
+        env.set_pairing(yaml=True)
+        env.pair_reset()
+        rb = ReplayBuffer(a.replay_size, 5, V + 2, V)
+        K, q = mask_schedule(10, V, 7, 7, 0.10, 0.25, 200)
+        frozen = torch.ones(E, dtype=torch.int32, device=dev)
+        ctr = [0]
+
+    def driver_step():
+        first = ctr[0] % 100 == 0
+        ctr[0] += 1
+        if first:
+            env.pair_reset()
+        env.observe(out=obs)
+        x = obs.to(torch.bfloat16) if a.actor_dtype == "bf16" else obs
+        raw = actors(x).float()
+        act = env.map_actions(raw)
+        part_v, ng_v = env.pair_noma(act, K, q, recalc_mask=first, reuse=None if first else frozen)
+        probs = actors.intent(env.pair_mask)
+        env.step_marl(act, part_v, ng_v)
+        env.observe(out=obs2)
+        rb.store_marl(obs, probs, raw, env.reward, env.reward_user, obs2, done=(ctr[0] % 100 == 0),
+                      mask_u8=env.pair_mask)
+
     def step():
+        if a.driver:
+            return driver_step()
         env.observe(out=obs)
         x = obs.to(torch.bfloat16) if a.actor_dtype == "bf16" else obs
         act = env.map_actions(actors(x).float())
@@ -74,11 +116,14 @@ def main():
 
     for _ in range(5):
         step()
-    res = {"config": {"envs": E, "V": V, "M": M, "steps": a.steps, "actor": "8 x MLP 5-512-256-2 (bmm), " + a.actor_dtype}}
+    res = {"config": {"envs": E, "V": V, "M": M, "steps": a.steps, "actor": "8 x MLP 5-512-256-2 (bmm), " + a.actor_dtype,
+                      "driver_loop": bool(a.driver)}}
     sec = timed(step, a.steps)
     res["eager_env_steps_per_s"] = E * a.steps / sec
     res["eager_us_per_step"] = sec / a.steps * 1e6
     try:
+        if a.driver:
+            raise RuntimeError("graph replay skipped: the driver loop branches on the step counter")
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
@@ -91,6 +136,9 @@ def main():
         res["graph_us_per_step"] = sec / a.steps * 1e6
     except Exception as exc:  # capture is best-effort
         res["graph_error"] = repr(exc)[:200]
+    if a.driver:
+        res["replay_rows"] = rb.mem_cntr
+        res["pairs_mean"] = float(env.noma_npairs.float().mean())
     res["mean_reward"] = float(env.reward.mean())
     print(json.dumps(res))
 

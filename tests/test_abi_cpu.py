@@ -97,3 +97,38 @@ def test_header_and_ctypes_agree_on_record_sizes(lib):
     assert n_stat == _lib.NSTAT and len(_lib.STAT_COLUMNS) == 13
     fields = re.findall(r"^\s+RISVEC_F_([A-Z_]+)", src, flags=re.M)
     assert len([f for f in fields if f != "COUNT"]) == len(_lib.FIELDS)
+
+
+def test_pairing_defaults_round_trip_through_the_struct(lib):
+    """`risvec_default_pairing` fills every field of `risvec_pairing_t`; reading them back through the
+    ctypes mirror checks that both sides agree on the layout (marl_train_bcd.py:435-441,489,1404-1498)."""
+    p = _lib.Pairing()
+    assert lib.risvec_default_pairing(8, 0, C.byref(p)) == 0
+    assert (p.min_pair_target, p.mwm_backoff_rounds, p.relax_topk_step, p.qos_enable) == (2, 5, 1, 1)
+    assert (p.mwm_accept_quantile, p.mwm_accept_q_step, p.completion_min_quantile) == (0.10, 0.05, 0.30)
+    assert (p.relax_tau_factor_per_round, p.tau_back_floor_db) == (0.95, 3.0)
+    assert (p.score_w_delta_db, p.score_w_history, p.qos_soft_penalty_dbscore, p.pair_hist_decay) == (1.0, 0.3, 6.0, 0.97)
+    assert p.abs_gain_min_db == float("-inf")
+    assert lib.risvec_default_pairing(8, 1, C.byref(p)) == 0
+    assert (p.min_pair_target, p.mwm_backoff_rounds, p.abs_gain_min_db) == (3, 3, -120.0)
+    assert lib.risvec_default_pairing(3, 0, C.byref(p)) == 0 and p.min_pair_target == 1
+    assert lib.risvec_default_pairing(0, 0, C.byref(p)) == -1
+    assert lib.risvec_pair_noma(None, C.byref(p), None, 8, 7, 0.2, 1, None, 1, None) == -1
+    assert lib.risvec_pair_reset(None, None) == -1
+    src = open(os.path.join(ROOT, "include", "risvec.h")).read()
+    assert int(re.search(r"#define RISVEC_PAIR_MAX_V (\d+)", src).group(1)) == _lib.PAIR_MAX_V
+
+
+def test_replay_entry_points_validate_arguments(lib):
+    h = C.c_void_p()
+    assert lib.risvec_replay_create(0, 0, 5, 10, 8, C.byref(h)) == -1
+    assert lib.risvec_replay_create(0, 16, 5, 10, 8, None) == -1
+    assert lib.risvec_replay_count(None) == 0
+    assert lib.risvec_replay_destroy(None) == 0
+    assert lib.risvec_replay_store(None, 1, None, None, None, None, None, None, 0, None, None) == -1
+    assert lib.risvec_replay_sample(None, 1, None, None, None, None, None, None, None, None, None) == -1
+    import torch
+
+    if not torch.cuda.is_available():
+        rc = lib.risvec_replay_create(0, 16, 5, 10, 8, C.byref(h))
+        assert rc == -4 and b"no CPU fallback" in lib.risvec_last_error()

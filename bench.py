@@ -265,6 +265,8 @@ def main():
     # SARL streams through the library's packed (tiled) records; MARL through the per-array entry
     # points, which measure faster for its 3-in / 6-out streams
     packed = wl == "sarl" and V == 8 and M in (16, 40) and E % 4 == 0
+    if os.environ.get("RISVEC_BENCH_MARL_PACKED") == "1" and wl == "marl" and V == 8 and E % 4 == 0:
+        packed = True   # A/B switch (profiles/r1_summary.md)
     stats_sum = torch.zeros(17, dtype=torch.float64, device=dev)
     if packed:
         in_rec = env.pack_inputs(actions, arrivals, phases)
@@ -272,8 +274,10 @@ def main():
         reward = torch.empty(T, E, dtype=torch.float32, device=dev)
         del actions, arrivals, phases
 
+        pk_groups = (partner, ngroups) if wl == "marl" else (None, None)
+
         def one_step():
-            env.rollout_packed(in_rec, out_rec=out_rec, reward=reward)
+            env.rollout_packed(in_rec, *pk_groups, out_rec=out_rec, reward=reward)
     else:
         out = env._alloc_traces(trace_names, T, trace_names)
 
@@ -347,7 +351,11 @@ def main():
         h_in = in_rec.cpu().pin_memory()
         h_out = torch.empty(out_rec.shape, dtype=torch.float32).pin_memory()
         h_rew = torch.empty(reward.shape, dtype=torch.float32).pin_memory()
-        run_host = lambda: env.rollout_packed_host(h_in, h_out, h_rew)
+        if wl == "marl":
+            h_pt, h_ng = partner.cpu().pin_memory(), ngroups.cpu().pin_memory()
+            run_host = lambda: env.rollout_packed_host(h_in, h_out, h_rew, h_pt, h_ng)
+        else:
+            run_host = lambda: env.rollout_packed_host(h_in, h_out, h_rew)
         h2d, d2h = h_in.numel() * 4, h_out.numel() * 4 + h_rew.numel() * 4
     else:
         h_act, h_arr = actions.cpu().pin_memory(), arrivals.cpu().pin_memory()

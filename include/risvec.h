@@ -98,6 +98,7 @@ enum risvec_field {
     RISVEC_F_STATS,          /* f32 [E,RISVEC_NSTAT] last_* scalars of the last step     */
     RISVEC_F_LAST_POWER,     /* f32 [E,2,V] last_power_W                                 */
     RISVEC_F_STEP_CTR,       /* i64 [E]    steps taken (keys the on-device RNG)          */
+    RISVEC_F_V2I_SHADOWING,  /* f64 [E,V]  V2I_Shadowing drawn at reset (MARL:409); read only by risvec_direct_link */
     /* NOMA pairing stage of the MARL driver (risvec_pair_noma) */
     RISVEC_F_PAIR_HIST,      /* f32 [E,V*V] pair_affinity_hist (marl_train_bcd.py:1288)  */
     RISVEC_F_PAIR_STREAK,    /* i32 [E,V]  unpaired_streak (:1290)                       */
@@ -251,6 +252,19 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
  * action [E,2,V] and phase [E,M] radians. */
 int risvec_observe(risvec_env_t* env, float* obs, void* stream);
 int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float* phase, void* stream);
+
+/* Random_phase (MARL:203-206; not called by the shipped drivers): every element gets one of the
+ * 2^control_bit quantised angles linspace(0, 2 pi, n, endpoint=False)[k] (:169).  idx [E,M] i32
+ * (device) injects the choices k (python `random.choice` in the reference); NULL draws them on the
+ * device (Philox). */
+int risvec_random_phase(risvec_env_t* env, const int32_t* idx, void* stream);
+/* The direct V2I link that the reference defines but never calls:
+ * path_loss [E,V] f64 = get_path_loss(position) in dB (MARL:192-196); shadowing [E,V] f64 =
+ * get_shadowing(delta_distance = velocity * time_slow, vehicle) (MARL:198-201) from the
+ * RISVEC_F_V2I_SHADOWING state and one N(0, 8) draw per vehicle (normals [E,V] f64 injected, or
+ * NULL: Philox).  Either output may be NULL.  Nothing on the step path reads these (as in the
+ * reference); RISVEC_F_V2I_SHADOWING is written by the caller (compat: the numpy draw of :409). */
+int risvec_direct_link(risvec_env_t* env, const double* normals, double* path_loss, double* shadowing, void* stream);
 
 /* ---- NOMA pairing: the stage that builds `noma_groups` for Environ.step ----
  * Knobs of the pairing pipeline; defaults = Config.__init__ and the getattr fall-backs at the call

@@ -474,6 +474,29 @@ class EnvOracle:
         self.elements_phase_shift_real = ph
         self.elements_phase_shift_complex = np.exp(ph * 1j)
 
+    def random_phase(self, indices):
+        """`Random_phase` (MARL/Environment.py:203-206) with the `random.choice` picks injected:
+        `indices` [E, M] into `possible_angles = linspace(0, 2 pi, 2**control_bit, endpoint=False)` (:169)."""
+        ph = self.possible_angles[np.asarray(indices, dtype=np.int64).reshape(self.E, self.M)]
+        self.elements_phase_shift_real = ph
+        self.elements_phase_shift_complex = np.exp(ph * 1j)
+
+    # ------------------------------------------------- direct V2I link (row a9, dead code in the reference)
+    def path_loss(self):
+        """`get_path_loss(position)` (MARL/Environment.py:192-196) for every vehicle -> [E, V] dB."""
+        d1 = np.abs(self.pos[..., 0] - BS_XYZ[0])
+        d2 = np.abs(self.pos[..., 1] - BS_XYZ[1])
+        dist = np.hypot(d1, d2)
+        return 128.1 + 37.6 * np.log10(np.sqrt(dist ** 2 + (BS_XYZ[2] - 1.5) ** 2) / 1000)
+
+    def shadowing(self, v2i_shadowing, normals8):
+        """`get_shadowing(delta_distance, vehicle)` (MARL/Environment.py:198-201) for every vehicle with
+        `delta_distance = velocity * time_slow` (:410); `normals8` are the N(0, 8) draws."""
+        dd = self.vel.astype(float) * self.p.time_slow
+        dec = 10  # Decorrelation_distance (:86)
+        return (np.multiply(np.exp(-1 * (dd / dec)), np.asarray(v2i_shadowing, float))
+                + np.sqrt(1 - np.exp(-2 * (dd / dec))) * np.asarray(normals8, float))
+
     # ------------------------------------------------------------------- BCD (row a6)
     def _objective(self):
         """MARL/Environment.py:222-231: note that `img` is the sum over ALL vehicles and

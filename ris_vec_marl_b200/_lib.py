@@ -42,7 +42,7 @@ STAT_COLUMNS = ("delay_mean", "energy_mean", "delay_local_mean", "delay_edge_q_m
 FIELDS = ("pos_x", "pos_y", "dir", "vel", "dist", "angle", "amp", "theta_re", "theta_im", "phase_real", "gains",
           "DataBuf", "data_t", "data_p", "over_data", "over_power", "vehicle_rate", "data_r", "reward_user",
           "reward", "mec_queue_cycles", "stats", "last_power_W", "step_ctr",
-          "pair_hist", "unpaired_streak", "pair_tau", "pair_k", "pair_mask", "pair_rounds",
+          "V2I_Shadowing", "pair_hist", "unpaired_streak", "pair_tau", "pair_k", "pair_mask", "pair_rounds",
           "noma_partner", "noma_ngroups", "noma_pairs", "noma_npairs")
 PAIR_MAX_V = 12
 REPLAY_FIELDS = ("state_memory", "action_memory", "reward_global_memory", "reward_local_memory", "new_state_memory",
@@ -139,6 +139,8 @@ EXPORTS = {
                                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_map_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "risvec_random_phase": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "risvec_direct_link": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_default_pairing": (C.c_int, [C.c_int, C.c_int, C.POINTER(Pairing)]),
     "risvec_pair_noma": (C.c_int, [C.c_void_p, C.POINTER(Pairing), C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int,
                                    C.c_void_p, C.c_int, C.c_void_p]),

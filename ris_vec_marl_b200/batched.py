@@ -208,6 +208,27 @@ class BatchedEnviron:
         ph = self._dev(action_phase, torch.float32, (self.E, self.M))
         check(self._lib.risvec_set_phase(self._h, self._p(ph), self.stream))
 
+    def Random_phase(self, indices=None):
+        """`Random_phase` (MARL/Environment.py:203-206): quantised random RIS phases; `indices` [E,M]
+        int32 injects the choices, None draws them on the device."""
+        ix = self._dev(indices, torch.int32, (self.E, self.M))
+        check(self._lib.risvec_random_phase(self._h, self._p(ix), self.stream))
+
+    def get_path_loss(self):
+        """`get_path_loss` (MARL/Environment.py:192-196) of every vehicle -> [E,V] float64 dB."""
+        out = torch.empty(self.E, self.V, dtype=torch.float64, device=self.device)
+        check(self._lib.risvec_direct_link(self._h, None, self._p(out), None, self.stream))
+        return out
+
+    def get_shadowing(self, normals=None):
+        """`get_shadowing(delta_distance, vehicle)` (MARL/Environment.py:198-201) of every vehicle with
+        `delta_distance = velocity * time_slow` (:410) -> [E,V] float64; `normals` [E,V] are the
+        N(0, 8) draws (None: on-device Philox).  Reads the `V2I_Shadowing` state field."""
+        nz = self._dev(normals, torch.float64, (self.E, self.V))
+        out = torch.empty(self.E, self.V, dtype=torch.float64, device=self.device)
+        check(self._lib.risvec_direct_link(self._h, self._p(nz), None, self._p(out), self.stream))
+        return out
+
     def optimize_phase_shift(self):
         check(self._lib.risvec_optimize_phase_shift(self._h, self.stream))
 

@@ -137,10 +137,11 @@ class _EnvironBase:
             dirs.append(_DIR_CHARS.index(_pyrandom.choice("dulr")))
             ints.append(np.random.randint(0, self.height))
             ints.append(np.random.randint(15, 20))
-        np.random.normal(0, 8, V)  # V2I_Shadowing: dead state, but it advances the stream (:409)
+        self.V2I_Shadowing = np.random.normal(0, 8, V)  # (:409) read only by get_shadowing
         ints.append(np.random.randint(5, int(self._b.params.data_buf_size) - 1))
         self._b.make_new_game(np.asarray(ints, dtype=np.int32)[None],
                               np.asarray(dirs, dtype=np.int32)[None] if dirs else None)
+        self._b.V2I_Shadowing.copy_(torch.as_tensor(self.V2I_Shadowing[None], device=self._b.device))
         self.vehicles = [Vehicle([0.0, 0.0], "d", 0) for _ in range(V)]
         self._pull()
 
@@ -193,6 +194,30 @@ class _EnvironBase:
 
     def get_channel_gains(self):
         return self._host["channel_gains"]
+
+    def Random_phase(self):
+        """MARL/Environment.py:203-206: M picks of python's `random.choice(possible_angles)`."""
+        n = 2 ** self.control_bit
+        idx = np.array([_pyrandom.choice(range(n)) for _ in range(self.M)], dtype=np.int32)
+        self._flush()
+        self._b.Random_phase(idx[None])
+        self._pull()
+
+    def get_path_loss(self, position_A):
+        """MARL/Environment.py:192-196 (never called by the drivers).  The device computes it for the
+        env's own vehicles; an arbitrary position is evaluated against them first."""
+        pl = self._b.get_path_loss()[0].cpu().numpy()
+        for i, veh in enumerate(self.vehicles):
+            if veh.position[0] == position_A[0] and veh.position[1] == position_A[1]:
+                return pl[i]
+        raise ValueError("get_path_loss is only available for the positions of the env's vehicles")
+
+    def get_shadowing(self, delta_distance, vehicle):
+        """MARL/Environment.py:198-201 for `delta_distance = velocity * time_slow` (the only value the
+        reference ever forms, :410); consumes one `np.random.normal(0, 8, 1)` like the reference."""
+        nz = np.zeros((1, self.n_veh))
+        nz[0, vehicle] = np.random.normal(0, 8, 1)[0]
+        return self._b.get_shadowing(nz)[0, vehicle].cpu().numpy().reshape(1)
 
     def _arrivals(self):
         lam = float(self._b.params.rate)

@@ -17,6 +17,57 @@ __global__ void k_set_phase(Dims d, State s, const float* __restrict__ phase) {
     s.theta_im[ix] = sn;
 }
 
+// Random_phase (MARL:203-206): theta_real[m] = possible_angles[k], k uniform in [0, 2^control_bit)
+// (injected `idx`, or Philox when NULL); possible_angles = linspace(0, 2 pi, n, endpoint=False)
+// (:169) = k * (2 pi / n).  theta_c = exp(j * theta_real) in float64.
+__global__ void k_random_phase(Dims d, State s, const int* __restrict__ idx, unsigned long long call) {
+    const size_t ix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= (size_t)d.E * d.M) return;
+    const int e = (int)(ix / d.M), m = (int)(ix - (size_t)e * d.M);
+    int k;
+    if (idx != nullptr) k = idx[ix];
+    else k = (int)(rng_draw(d, e, call, (unsigned)m, kRngChannel).x % (unsigned)d.ncand);
+    k = min(max(k, 0), d.ncand - 1);
+    const double step = __ddiv_rn(2.0 * 3.14159265358979323846, (double)d.ncand);
+    const double ang = __dmul_rn((double)k, step);
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    s.phase_real[ix] = (float)ang;
+    s.theta_re[ix] = cs;
+    s.theta_im[ix] = sn;
+}
+
+// The direct V2I link the reference defines but never calls: get_path_loss (MARL:192-196) and
+// get_shadowing (MARL:198-201, AR(1) over delta_distance = velocity * time_slow (:410) with the
+// V2I_Shadowing drawn at reset (:409) and one N(0, 8) draw), for every vehicle.
+__global__ void k_direct_link(Dims d, State s, risvec_params_t p, const double* __restrict__ shadow_state,
+                              const double* __restrict__ normals, double* __restrict__ path_loss,
+                              double* __restrict__ shadowing, unsigned long long call) {
+    const size_t ix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= (size_t)d.E * d.V) return;
+    const int e = (int)(ix / d.V), v = (int)(ix - (size_t)e * d.V);
+    if (path_loss != nullptr) {
+        const double dist = hypot(fabs(s.pos_x[ix] - kBsX), fabs(s.pos_y[ix] - kBsY));
+        const double hz = kBsZ - 1.5;
+        const double d3 = sqrt(__dadd_rn(__dmul_rn(dist, dist), __dmul_rn(hz, hz)));
+        path_loss[ix] = __dadd_rn(128.1, __dmul_rn(37.6, log10(__ddiv_rn(d3, 1000.0))));
+    }
+    if (shadowing != nullptr) {
+        double n8;
+        if (normals != nullptr) n8 = normals[ix];
+        else {  // Box-Muller from two Philox uniforms, sigma = 8 dB
+            const uint4 r = rng_draw(d, e, call, (unsigned)v, kRngChannel);
+            const double u1 = fmax(u01d(r.x, r.y), 1e-300), u2 = u01d(r.z, r.w);
+            n8 = 8.0 * sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        }
+        const double dd = __dmul_rn((double)s.vel[ix], p.time_slow);
+        const double r = __ddiv_rn(dd, 10.0);  // Decorrelation_distance = 10 (MARL:86)
+        const double a = exp(__dmul_rn(-1.0, r));
+        const double b = sqrt(__dsub_rn(1.0, exp(__dmul_rn(-2.0, r))));
+        shadowing[ix] = __dadd_rn(__dmul_rn(a, shadow_state[ix]), __dmul_rn(b, n8));
+    }
+}
+
 // Geometry phasor of vehicle v and element m:
 //   phases_R_i[v][m] * phase_R[m] = exp(-j*pi*angle_v*m) * exp(+j*pi*angle_BR*m)   (MARL:179,253)
 // evaluated as sincospi(m * (angle_BR - angle_v)) -- sincospi reduces its argument exactly.

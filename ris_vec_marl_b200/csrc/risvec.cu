@@ -335,6 +335,7 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
         {RISVEC_F_REWARD_USER, E, V, 4, 1}, {RISVEC_F_REWARD, E, 1, 4, 1}, {RISVEC_F_MECQ, E, 1, 8, 1},
         {RISVEC_F_STATS, E, RISVEC_NSTAT, 4, 1}, {RISVEC_F_LAST_POWER, E, 2 * V, 4, 1},
         {RISVEC_F_STEP_CTR, E, 1, 8, 0},
+        {RISVEC_F_V2I_SHADOWING, E, V, 8, 1},
         {RISVEC_F_PAIR_HIST, E, V * V, 4, 1}, {RISVEC_F_PAIR_STREAK, E, V, 4, 0}, {RISVEC_F_PAIR_TAU, E, 1, 8, 1},
         {RISVEC_F_PAIR_K, E, 1, 4, 0}, {RISVEC_F_PAIR_MASK, E, V * V, 1, 0}, {RISVEC_F_PAIR_ROUNDS, E, 1, 4, 0},
         {RISVEC_F_NOMA_PARTNER, E, V, 4, 0}, {RISVEC_F_NOMA_NGROUPS, E, 1, 4, 0}, {RISVEC_F_NOMA_PAIRS, E, V, 4, 0},
@@ -854,6 +855,25 @@ int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float
     const long long n = (long long)d.E * (2 * d.V + d.M);
     k_map_actions_sarl<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, raw, action, phase);
     return check_launch(env, "k_map_actions_sarl");
+}
+
+int risvec_random_phase(risvec_env_t* env, const int32_t* idx, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const long long n = (long long)env->dims.E * env->dims.M;
+    k_random_phase<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, idx, env->chan_calls++);
+    return check_launch(env, "k_random_phase");
+}
+
+int risvec_direct_link(risvec_env_t* env, const double* normals, double* path_loss, double* shadowing, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (!path_loss && !shadowing) return fail(RISVEC_ERR_INVALID, "both outputs are NULL");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const long long n = (long long)env->dims.E * env->dims.V;
+    const double* shadow_state = (const double*)(env->arena + env->fields[RISVEC_F_V2I_SHADOWING].offset);
+    k_direct_link<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, shadow_state,
+                                                                       normals, path_loss, shadowing, env->chan_calls++);
+    return check_launch(env, "k_direct_link");
 }
 
 int risvec_default_pairing(int n_veh, int yaml, risvec_pairing_t* out) {

@@ -65,7 +65,7 @@ struct risvec_env {
     size_t scratch_bytes;
     int pipe_ready;
     cudaStream_t s_in, s_out;
-    cudaEvent_t ev[2 * 16 + 2];
+    cudaEvent_t ev[2 * 64 + 2];  // 2 * kMaxChunks + 2
     int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
 };
 
@@ -372,7 +372,7 @@ int risvec_destroy(risvec_env_t* env) {
     if (env->pipe_ready) {
         cudaStreamDestroy(env->s_in);
         cudaStreamDestroy(env->s_out);
-        for (int i = 0; i < 2 * 16 + 2; ++i) cudaEventDestroy(env->ev[i]);
+        for (int i = 0; i < 2 * 64 + 2; ++i) cudaEventDestroy(env->ev[i]);
     }
     delete env;
     return RISVEC_OK;
@@ -585,7 +585,7 @@ int risvec_rollout_marl_packed(risvec_env_t* env, int T, const void* in_rec, con
 // chunk c-1 is copied out (D2H engine), so the call runs at PCIe speed of the larger direction.
 namespace {
 
-constexpr int kMaxChunks = 16;
+constexpr int kMaxChunks = 64;
 
 int ensure_pipe(risvec_env* env) {
     if (env->pipe_ready) return RISVEC_OK;
@@ -598,8 +598,9 @@ int ensure_pipe(risvec_env* env) {
 }
 
 int chunk_steps(int T, size_t in_bytes_per_step) {
-    // ~24 MB of input per chunk, at most kMaxChunks chunks
-    size_t per = (size_t)24 << 20;
+    // ~RISVEC_HOST_CHUNK_MB (default 24) MB of input per chunk, at most kMaxChunks chunks
+    static const int mb = [] { const char* v = getenv("RISVEC_HOST_CHUNK_MB"); int m = v ? atoi(v) : 24; return m < 1 ? 1 : m; }();
+    size_t per = (size_t)mb << 20;
     int tc = (int)(per / (in_bytes_per_step ? in_bytes_per_step : 1));
     if (tc < 1) tc = 1;
     int n = (T + tc - 1) / tc;

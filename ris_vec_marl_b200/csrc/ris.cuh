@@ -108,36 +108,52 @@ __global__ void k_bcd(Dims d, State s) {
     sr = seg_sum<32>(sr);
     si = seg_sum<32>(si);
     __syncwarp();
+    // candidates: up to 32 -> lane k owns candidate k and its e_k = exp(j 2 pi k / ncand) is formed
+    // once; more -> lanes stride over them.  The arg-max (first maximum wins) is reduced on
+    // (value, k) only, over the 2^ceil(log2 ncand) lanes that hold candidates; the winner's partial
+    // sums are then fetched from its lane.
+    const bool one = d.ncand <= 32;
+    double er0 = 0.0, ei0 = 0.0;
+    if (one && lane < d.ncand) sincospi(2.0 * (double)lane / (double)d.ncand, &ei0, &er0);
+    int width = 32;
+    if (one) { width = 1; while (width < d.ncand) width <<= 1; }
     for (int m = 0; m < M; ++m) {
         const double2 cm = c[m], tm = th[m];
         const double rr = sr - (tm.x * cm.x - tm.y * cm.y);
         const double ri = si - (tm.x * cm.y + tm.y * cm.x);
-        // each lane scores candidates k = lane, lane + 32, ...
         double best = -1.0, bsr = rr, bsi = ri, ber = 0.0, bei = 0.0;
         int bk = 0x7fffffff;
-        for (int k = lane; k < d.ncand; k += 32) {
-            double er, ei;
-            sincospi(2.0 * (double)k / (double)d.ncand, &ei, &er);
-            const double cr = rr + (er * cm.x - ei * cm.y);
-            const double ci = ri + (er * cm.y + ei * cm.x);
-            const double val = cr * cr + ci * ci;
-            if (val > best) {
-                best = val; bk = k; bsr = cr; bsi = ci; ber = er; bei = ei;
+        if (one) {
+            if (lane < d.ncand) {
+                const double cr = rr + (er0 * cm.x - ei0 * cm.y);
+                const double ci = ri + (er0 * cm.y + ei0 * cm.x);
+                const double val = cr * cr + ci * ci;
+                if (val > best) { best = val; bk = lane; bsr = cr; bsi = ci; ber = er0; bei = ei0; }
+            }
+        } else {
+            for (int k = lane; k < d.ncand; k += 32) {
+                double er, ei;
+                sincospi(2.0 * (double)k / (double)d.ncand, &ei, &er);
+                const double cr = rr + (er * cm.x - ei * cm.y);
+                const double ci = ri + (er * cm.y + ei * cm.x);
+                const double val = cr * cr + ci * ci;
+                if (val > best) { best = val; bk = k; bsr = cr; bsi = ci; ber = er; bei = ei; }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(kFull, best, o);
-            const int ok = __shfl_xor_sync(kFull, bk, o);
-            const double osr = __shfl_xor_sync(kFull, bsr, o), osi = __shfl_xor_sync(kFull, bsi, o);
-            const double oer = __shfl_xor_sync(kFull, ber, o), oei = __shfl_xor_sync(kFull, bei, o);
-            if (ov > best || (ov == best && ok < bk)) {
-                best = ov; bk = ok; bsr = osr; bsi = osi; ber = oer; bei = oei;
-            }
+        double wv = best;
+        int wk = bk;
+        for (int o = width >> 1; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(kFull, wv, o);
+            const int ok = __shfl_xor_sync(kFull, wk, o);
+            if (ov > wv || (ov == wv && ok < wk)) { wv = ov; wk = ok; }
         }
-        if (best > 0.0) {
-            sr = bsr; si = bsi;
-            if (lane == 0) th[m] = make_double2(ber, bei);
+        wv = __shfl_sync(kFull, wv, 0);
+        wk = __shfl_sync(kFull, wk, 0);
+        if (wv > 0.0) {
+            const int src = wk & 31;   // the lane whose own best candidate is the winner
+            sr = __shfl_sync(kFull, bsr, src);
+            si = __shfl_sync(kFull, bsi, src);
+            if (lane == src) th[m] = make_double2(ber, bei);
         } else {  // never improved on best = 0: the reference stores the integer 0
             sr = rr; si = ri;
             if (lane == 0) th[m] = make_double2(0.0, 0.0);

@@ -60,6 +60,8 @@ struct PairCtx {
 
     __device__ void carve(unsigned char* base, int ln) {
         lane = ln;
+        s_ranked = false;
+        rn = 0;
         gl = (double*)base; pw = gl + N; g15 = pw + N; g12 = g15 + N;
         S = g12 + N; W = S + NN; dp = W + NN; slot = dp + NS;
         Hs = (float*)(slot + 2);
@@ -74,12 +76,42 @@ struct PairCtx {
         return v;
     }
 
-    // numpy.quantile(vals[valid], q, method="linear") incl. numpy's two-sided _lerp; n -> count.
-    // `vals` must hold +inf wherever `valid` is 0 (so invalid entries never rank below a valid one).
-    __device__ double quantile(const double* vals, double q, int& n) {
+    // Order statistics by counting.  rank_pass: every lane keeps its ceil(N^2 / 32) entries of `vals`
+    // in registers and counts, over one broadcast pass of the array, how many values are smaller
+    // (rl) and how many are equal (re): an entry is the k-th order statistic iff rl <= k < rl + re.
+    // `vals` must hold +inf wherever `valid` is 0.  The counts stay valid until the array changes,
+    // so several quantiles of the same values (the matching's accept threshold and the
+    // completion's threshold, :346 and :300) cost one pass.
+    static constexpr int EPL = (NN + 31) / 32;
+    double rv[EPL];
+    int rl[EPL], re[EPL], rn;
+
+    __device__ void rank_pass(const double* vals) {
         int c = 0;
         for (int e = lane; e < NN; e += 32) c += valid[e] ? 1 : 0;
-        n = wsum(c);
+        rn = wsum(c);
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int e = lane + 32 * k;
+            rv[k] = e < NN ? vals[e] : CUDART_INF;
+            rl[k] = 0;
+            re[k] = 0;
+        }
+        if (rn == 0) return;
+#pragma unroll 8
+        for (int o = 0; o < NN; ++o) {
+            const double u = vals[o];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                rl[k] += u < rv[k];
+                re[k] += u == rv[k];
+            }
+        }
+    }
+
+    // numpy.quantile(values of the last rank_pass, q, method="linear") incl. numpy's two-sided _lerp
+    __device__ double select(double q) {
+        const int n = rn;
         if (n == 0) return 0.0;
         const double vi = __dmul_rn((double)(n - 1), q);
         int lo, hi;
@@ -87,28 +119,12 @@ struct PairCtx {
         if (vi >= (double)(n - 1)) lo = hi = n - 1;
         else if (vi < 0.0) lo = hi = 0;
         else { const double f = floor(vi); lo = (int)f; hi = lo + 1; t = __dsub_rn(vi, f); }
-        constexpr int EPL = (NN + 31) / 32;     // entries per lane
-        double v[EPL];
-        int r[EPL];
 #pragma unroll
         for (int k = 0; k < EPL; ++k) {
             const int e = lane + 32 * k;
-            v[k] = e < NN ? vals[e] : CUDART_INF;
-            r[k] = 0;
-        }
-        // rank = #(u < v) + #(u == v, o < e): "<=" below the own index, "<" above it
-#pragma unroll 8
-        for (int o = 0; o < NN; ++o) {
-            const double u = vals[o];
-#pragma unroll
-            for (int k = 0; k < EPL; ++k) r[k] += (o < lane + 32 * k) ? (u <= v[k]) : (u < v[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < EPL; ++k) {
-            const int e = lane + 32 * k;
-            if (e < NN && valid[e]) {
-                if (r[k] == lo) slot[0] = v[k];
-                if (r[k] == hi) slot[1] = v[k];
+            if (e < NN && valid[e]) {   // equal values may be published by several lanes: same bits
+                if (rl[k] <= lo && lo < rl[k] + re[k]) slot[0] = rv[k];
+                if (rl[k] <= hi && hi < rl[k] + re[k]) slot[1] = rv[k];
             }
         }
         __syncwarp();
@@ -137,9 +153,9 @@ struct PairCtx {
             W[e] = ok ? fabs(__dsub_rn(g15[i], g15[j])) : CUDART_INF;
         }
         __syncwarp();
-        int n;
-        const double tau = quantile(W, q, n);
-        return n ? tau : 0.0;
+        rank_pass(W);
+        s_ranked = false;
+        return rn ? select(q) : 0.0;
     }
 
     // _build_feasible_mask_from_delta_g (:134-156) -> feas
@@ -200,6 +216,7 @@ struct PairCtx {
     // _score_matrix_from_gain_and_history (:164-194) -> S
     __device__ void score(const PairArgs& a) {
         const double ninf = -CUDART_INF;
+        s_ranked = false;
         bool any = false;
         for (int e = lane; e < NN; e += 32) {
             const int i = e / N, j = e - i * N;
@@ -244,14 +261,19 @@ struct PairCtx {
         __syncwarp();
     }
 
-    // S with +inf in place of the non-edges -> W (the layout `quantile` wants); valid = edge
-    __device__ void stage_edges() {
+    // ranks of the finite entries of S (edges); cached until `score` rewrites S
+    bool s_ranked;
+    __device__ void rank_edges() {
+        if (s_ranked) return;
         for (int e = lane; e < NN; e += 32) {
             const bool ok = isfinite(S[e]);
             valid[e] = ok;
-            W[e] = ok ? S[e] : CUDART_INF;
+            W[e] = ok ? S[e] : CUDART_INF;    // +inf in place of the non-edges: the layout rank_pass wants
         }
         __syncwarp();
+        rank_pass(W);
+        __syncwarp();
+        s_ranked = true;
     }
 
     // _mwm_primary (:326-398), allow_singles = True.  Returns the number of pairs written to pr.
@@ -262,11 +284,10 @@ struct PairCtx {
     // W = -inf, and -inf + dp never beats the single option, which is the reference's `continue`.
     __device__ int mwm_primary(double accept_q) {
         const double ninf = -CUDART_INF;
-        stage_edges();
-        int n;
+        rank_edges();
+        if (rn == 0) return 0;
         const double q = fmin(fmax(accept_q, 0.0), 1.0);
-        const double thr = quantile(W, __dsub_rn(1.0, q), n);
-        if (n == 0) return 0;
+        const double thr = select(__dsub_rn(1.0, q));
         for (int e = lane; e < NN; e += 32) W[e] = (valid[e] && S[e] >= thr) ? S[e] : ninf;
         constexpr int full = NS - 1;
         if (lane == 0) { dp[full] = 0.0; ch[full] = -1; }
@@ -306,10 +327,9 @@ struct PairCtx {
 
     // _mwm_completion (:276-324): greedy top-up, candidates ordered by (S, i, j) descending
     __device__ int completion(int np, int min_pairs, double cq) {
-        stage_edges();
-        int n;
-        const double thr = quantile(W, cq, n);
-        if (n == 0) return np;
+        rank_edges();
+        if (rn == 0) return np;
+        const double thr = select(cq);
         unsigned occ = 0;
         for (int k = 0; k < 2 * np; ++k) occ |= 1u << pr[k];
         while (np < min_pairs) {

@@ -97,4 +97,24 @@ __device__ inline T seg_sum(T x) {
     return x;
 }
 
+// z = exp(j*pi*delta) evaluated ONCE per vehicle (sincospi) and raised by float64 complex
+// multiplications (each ~1e-16 relative), instead of one sincospi per table entry.
+__device__ __noinline__ double2 unit_phasor64(double delta) {
+    double s64, c64;
+    sincospi(delta, &s64, &c64);
+    return make_double2(c64, s64);
+}
+__device__ __forceinline__ double2 cmul64(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cpow64(double2 z, unsigned n) {  // z^n by squaring
+    double2 r = make_double2(1.0, 0.0);
+    while (n) {
+        if (n & 1u) r = cmul64(r, z);
+        z = cmul64(z, z);
+        n >>= 1;
+    }
+    return r;
+}
+
 }  // namespace risvec

@@ -166,6 +166,114 @@ __global__ void k_bcd(Dims d, State s) {
     }
 }
 
+// optimize_phase_shift for ncand <= 8, V <= 8 (every shipped configuration: control_bit = 3,
+// V = 8): one warp = 4 envs, lane = (env el, candidate k), so all 32 lanes score candidates in the
+// sequential element loop.  c_m = sum_v z_v^m is accumulated from ONE sincospi per lane
+// (z_v = exp(j pi (angle_BR - angle_v)) of vehicle v = k, shuffled to the env's lanes) and float64
+// complex powers: lane k owns the elements m = k + 8 i, w = z^k * (z^8)^i.  Same search, same
+// tie rule (first maximum), same acceptance test as k_bcd.
+__global__ void k_bcd_v8(Dims d, State s) {
+    extern __shared__ double2 bcd_smem[];
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, el = lane >> 3, k = lane & 7;
+    const int e_raw = (blockIdx.x * wpb + warp) * 4 + el;
+    const bool env_ok = e_raw < d.E;
+    const int e = min(e_raw, d.E - 1);
+    const int V = d.V, M = d.M, base = lane & ~7;
+    double2* c = bcd_smem + (size_t)(warp * 4 + el) * 2 * M;
+    double2* th = c + M;
+    const double2 my_z = unit_phasor64(d.angle_BR - s.angle[(size_t)e * V + min(k, V - 1)]);
+    for (int m = k; m < M; m += 8) c[m] = make_double2(0.0, 0.0);
+    for (int v = 0; v < V; ++v) {
+        const double2 z = make_double2(__shfl_sync(kFull, my_z.x, base + v), __shfl_sync(kFull, my_z.y, base + v));
+        double2 w = cpow64(z, (unsigned)k);
+        const double2 z2 = cmul64(z, z), z4 = cmul64(z2, z2), z8 = cmul64(z4, z4);
+        for (int m = k; m < M; m += 8) {
+            c[m].x += w.x;
+            c[m].y += w.y;
+            w = cmul64(w, z8);
+        }
+    }
+    double sr = 0.0, si = 0.0;
+    for (int m = k; m < M; m += 8) {
+        const double tr = s.theta_re[(size_t)e * M + m], ti = s.theta_im[(size_t)e * M + m];
+        const double2 cm = c[m];
+        th[m] = make_double2(tr, ti);
+        sr += tr * cm.x - ti * cm.y;
+        si += tr * cm.y + ti * cm.x;
+    }
+    sr = seg_sum<8>(sr);
+    si = seg_sum<8>(si);
+    __syncwarp();
+    double er0 = 0.0, ei0 = 0.0;
+    if (k < d.ncand) sincospi(2.0 * (double)k / (double)d.ncand, &ei0, &er0);
+    for (int m = 0; m < M; ++m) {
+        const double2 cm = c[m], tm = th[m];
+        const double rr = sr - (tm.x * cm.x - tm.y * cm.y);
+        const double ri = si - (tm.x * cm.y + tm.y * cm.x);
+        double best = -1.0, bsr = rr, bsi = ri;
+        int bk = 0x7fffffff;
+        if (k < d.ncand) {
+            const double cr = rr + (er0 * cm.x - ei0 * cm.y);
+            const double ci = ri + (er0 * cm.y + ei0 * cm.x);
+            const double val = cr * cr + ci * ci;
+            if (val > best) { best = val; bk = k; bsr = cr; bsi = ci; }
+        }
+        double wv = best;
+        int wk = bk;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(kFull, wv, o);
+            const int ok = __shfl_xor_sync(kFull, wk, o);
+            if (ov > wv || (ov == wv && ok < wk)) { wv = ov; wk = ok; }
+        }
+        // (wv, wk) is uniform over the env's 8 lanes after the butterfly; the 4 envs of the warp may
+        // decide differently, so the shuffles stay unconditional
+        const bool acc = wv > 0.0;
+        const int src = base + (acc ? (wk & 7) : 0);
+        const double nsr = __shfl_sync(kFull, bsr, src), nsi = __shfl_sync(kFull, bsi, src);
+        sr = acc ? nsr : rr;
+        si = acc ? nsi : ri;
+        if (acc) {
+            if (lane == src) th[m] = make_double2(er0, ei0);
+        } else if (k == 0) {  // never improved on best = 0: the reference stores the integer 0
+            th[m] = make_double2(0.0, 0.0);
+        }
+        __syncwarp();
+    }
+    if (env_ok)
+        for (int m = k; m < M; m += 8) {
+            s.theta_re[(size_t)e * M + m] = th[m].x;
+            s.theta_im[(size_t)e * M + m] = th[m].y;
+        }
+}
+
+// update_channel_gains, "free" model, lane = (env, vehicle): the vehicle's phasor z_v^m is stepped
+// by one float64 complex multiplication per element (re-anchored by an exact sincospi every 32
+// elements), the M products theta_m z_v^m are summed in order -- no shuffles at all.
+template <int VP>
+__global__ void k_gains_free_v(Dims d, State s) {
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int e_raw = (int)(gtid / VP), v = (int)(gtid % VP);
+    const bool act = e_raw < d.E && v < d.V;
+    const int e = min(e_raw, d.E - 1), M = d.M;
+    const size_t ev = (size_t)e * d.V + min(v, d.V - 1);
+    const double delta = d.angle_BR - s.angle[ev];
+    const double2 z = unit_phasor64(delta);
+    const double* tr = s.theta_re + (size_t)e * M;
+    const double* ti = s.theta_im + (size_t)e * M;
+    double sr = 0.0, si = 0.0;
+    double2 w = make_double2(1.0, 0.0);
+    for (int m = 0; m < M; ++m) {
+        if ((m & 31) == 0 && m) w = unit_phasor64((double)m * delta);
+        const double a = tr[m], b = ti[m];
+        sr += a * w.x - b * w.y;
+        si += a * w.y + b * w.x;
+        w = cmul64(w, z);
+    }
+    if (act) s.gains[ev] = s.amp[ev] * (sr * sr + si * si);
+}
+
 // update_channel_gains, "free" model (MARL:263-273): the cascaded RIS reduction
 //   gain_v = amp_v * | sum_m theta_m * phasor(v, m) |^2
 // one warp per env, lanes stride over the M elements, complex warp-shuffle reduction.

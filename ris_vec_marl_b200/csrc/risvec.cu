@@ -453,6 +453,16 @@ int risvec_set_phase(risvec_env_t* env, const float* phase, void* stream) {
 int risvec_optimize_phase_shift(risvec_env_t* env, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     CUDA_TRY(cudaSetDevice(env->device));
+    if (env->dims.ncand <= 8 && env->dims.V <= 8 && env->dims.M <= 256 && !env->force_generic) {
+        // 4 envs per warp, lane = (env, candidate)
+        const int wpb = env->dims.M <= 64 ? 4 : 1;
+        const int blocks = (env->dims.E + 4 * wpb - 1) / (4 * wpb);
+        const size_t smem = (size_t)wpb * 4 * 2 * env->dims.M * sizeof(double2);
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(k_bcd_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_bcd_v8<<<blocks, 32 * wpb, smem, (cudaStream_t)stream>>>(env->dims, env->st);
+        return check_launch(env, "k_bcd_v8");
+    }
     const int wpb = 4, threads = 32 * wpb, blocks = (env->dims.E + wpb - 1) / wpb;
     const size_t smem = (size_t)wpb * 2 * env->dims.M * sizeof(double2);
     if (smem > 48 * 1024)
@@ -466,6 +476,21 @@ int risvec_update_channel_gains(risvec_env_t* env, const double* chan_rand, cons
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     CUDA_TRY(cudaSetDevice(env->device));
     if (env->params.channel_model == RISVEC_CHANNEL_FREE) {
+        if (!env->force_generic) {  // lane = (env, vehicle), sequential over the elements
+            const int VP = pow2ceil(env->dims.V);
+            const long long n = (long long)env->dims.E * VP;
+            const int threads = 128, blocks = (int)((n + threads - 1) / threads);
+            cudaStream_t st = (cudaStream_t)stream;
+            switch (VP) {
+                case 1: k_gains_free_v<1><<<blocks, threads, 0, st>>>(env->dims, env->st); break;
+                case 2: k_gains_free_v<2><<<blocks, threads, 0, st>>>(env->dims, env->st); break;
+                case 4: k_gains_free_v<4><<<blocks, threads, 0, st>>>(env->dims, env->st); break;
+                case 8: k_gains_free_v<8><<<blocks, threads, 0, st>>>(env->dims, env->st); break;
+                case 16: k_gains_free_v<16><<<blocks, threads, 0, st>>>(env->dims, env->st); break;
+                default: k_gains_free_v<32><<<blocks, threads, 0, st>>>(env->dims, env->st); break;
+            }
+            return check_launch(env, "k_gains_free_v");
+        }
         const int wpb = 4, threads = 32 * wpb, blocks = (env->dims.E + wpb - 1) / wpb;
         k_gains_free<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st);
         return check_launch(env, "k_gains_free");

@@ -315,29 +315,10 @@ __device__ __noinline__ void phasor_f32(double x, float* re, float* im) {
 }
 
 // float64 complex helpers for building phasor tables: exp(j*pi*m*delta) = z^m with
-// z = exp(j*pi*delta) evaluated ONCE per vehicle (sincospi) and raised by float64 complex
-// multiplications (each ~1e-16 relative), instead of one sincospi per table entry.
-__device__ __noinline__ double2 unit_phasor64(double delta) {
-    double s64, c64;
-    sincospi(delta, &s64, &c64);
-    return make_double2(c64, s64);
-}
-__device__ __forceinline__ double2 cmul64(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cpow64(double2 z, unsigned n) {  // z^n by squaring
-    double2 r = make_double2(1.0, 0.0);
-    while (n) {
-        if (n & 1u) r = cmul64(r, z);
-        z = cmul64(z, z);
-        n >>= 1;
-    }
-    return r;
-}
-
 // Used when ONE warp serves an env group (M <= 40); larger M goes through k_sarl_cascade2 +
 // k_sarl_scan below (several warps per env: the per-vehicle phase would be a serial section of
 // one warp per block and step).
+
 template <int VP, int MPL, int WPE>
 __global__ void __launch_bounds__(32 * WPE) k_sarl_rollout(Dims d, State s, risvec_params_t p, SarlArgs a) {
     static_assert(MPL % 4 == 0, "elements are processed four at a time (LDS.128 + FFMA2 pairs)");

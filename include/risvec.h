@@ -298,11 +298,14 @@ int risvec_default_pairing(int n_veh, int yaml, risvec_pairing_t* out);
  * rounds; then noma_groups -> NOMA_PARTNER / NOMA_NGROUPS (feed them to risvec_rollout_marl),
  * NOMA_PAIRS / NOMA_NPAIRS, and the history / streak updates.  reuse [E] i32 (device, may be
  * NULL): != 0 keeps that env's frozen groups (:1542-1547) and only updates history / streak.
+ * new_episode != 0: the call is the first step of an episode -- history, streak and frozen groups are
+ * taken as cleared (what risvec_pair_reset does, without the extra launch); needs recalc_mask != 0.
  * V <= RISVEC_PAIR_MAX_V.  Results are exact (same pairs as the reference) up to float64 ulp
  * differences of log10 / log2 at non-structural near-ties; at exact ties numpy's argsort order is
  * taken as stable (lower index first). */
 int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float* p01, int64_t p01_env_stride,
-                     int topk, double tau_q, int recalc_mask, const int32_t* reuse, int decay, void* stream);
+                     int topk, double tau_q, int recalc_mask, const int32_t* reuse, int decay, int new_episode,
+                     void* stream);
 /* start of an episode (:1282-1297): history, streak, thresholds, mask and frozen groups cleared */
 int risvec_pair_reset(risvec_env_t* env, void* stream);
 

@@ -143,7 +143,7 @@ EXPORTS = {
     "risvec_direct_link": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_default_pairing": (C.c_int, [C.c_int, C.c_int, C.POINTER(Pairing)]),
     "risvec_pair_noma": (C.c_int, [C.c_void_p, C.POINTER(Pairing), C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int,
-                                   C.c_void_p, C.c_int, C.c_void_p]),
+                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "risvec_pair_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
     "risvec_replay_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "risvec_replay_destroy": (C.c_int, [C.c_void_p]),

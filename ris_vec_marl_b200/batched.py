@@ -413,11 +413,12 @@ class BatchedEnviron:
         """Start of an episode (marl_train_bcd.py:1282-1297)."""
         check(self._lib.risvec_pair_reset(self._h, self.stream))
 
-    def pair_noma(self, p01, topk, tau_q, recalc_mask=True, reuse=None, decay=True):
+    def pair_noma(self, p01, topk, tau_q, recalc_mask=True, reuse=None, decay=True, new_episode=False):
         """One driver step of the pairing stage (marl_train_bcd.py:1315-1561) for every env.
 
         `p01`: offload power in [0,1], either [E,V] or the env action [E,2,V] (row 0 is used).
-        `topk`, `tau_q`: K_now / q_now of the mask curriculum (`mask_schedule`).  Returns the
+        `topk`, `tau_q`: K_now / q_now of the mask curriculum (`mask_schedule`).  `new_episode=True`
+        makes the call the first step of an episode (`pair_reset` folded into the same launch).  Returns the
         zero-copy views `(noma_partner [E,V], noma_ngroups [E])` to hand to `rollout_marl`."""
         t = self._dev(p01, torch.float32)
         if tuple(t.shape) == (self.E, 2, self.V):
@@ -428,7 +429,8 @@ class BatchedEnviron:
             raise ValueError(f"p01 must be [E,V] or [E,2,V], got {tuple(t.shape)}")
         ru = self._dev(reuse, torch.int32, (self.E,))
         check(self._lib.risvec_pair_noma(self._h, C.byref(self.pairing), self._p(t), stride, int(topk), float(tau_q),
-                                         int(bool(recalc_mask)), self._p(ru), int(bool(decay)), self.stream))
+                                         int(bool(recalc_mask)), self._p(ru), int(bool(decay)), int(bool(new_episode)),
+                                         self.stream))
         return self._views["noma_partner"], self._views["noma_ngroups"]
 
     def shard_stats(self, out=None, accumulate=False):

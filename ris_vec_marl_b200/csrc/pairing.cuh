@@ -18,7 +18,7 @@ struct PairArgs {
     const int* reuse;        // [E] or NULL: != 0 -> frozen groups (:1542-1547), solve skipped
     int topk;                // K_now (:1324)
     double tau_q;            // q_now (:1329)
-    int recalc, decay;
+    int recalc, decay, fresh;   // fresh: first step of an episode (:1282-1297) -- history / streak start from zero
     int min_pairs, backoff_rounds;
     double accept_q, accept_q_step, completion_q;
     int relax_topk_step;
@@ -370,7 +370,7 @@ __global__ void k_pair_noma(Dims d, State s, PairArgs a) {
 
     float* H = a.hist + e * NN;
     for (int x = lane; x < NN; x += 32) {
-        const float h = H[x];
+        const float h = a.fresh ? 0.f : H[x];
         c.Hs[x] = a.decay ? __fmul_rn(h, a.decay_f) : h;     // :1406 (float32 array *= python float)
     }
     if (lane < N) {
@@ -398,7 +398,7 @@ __global__ void k_pair_noma(Dims d, State s, PairArgs a) {
     }
 
     int np = 0, rounds = 0;
-    const bool frozen = a.reuse != nullptr && a.reuse[e] != 0 && a.ngroups[e] > 0;
+    const bool frozen = !a.fresh && a.reuse != nullptr && a.reuse[e] != 0 && a.ngroups[e] > 0;
     if (frozen) {                                             // :1542-1547
         np = a.npairs[e];
         if (lane < 2 * np) c.pr[lane] = a.pairs[e * N + lane];
@@ -453,7 +453,7 @@ __global__ void k_pair_noma(Dims d, State s, PairArgs a) {
     for (int x = lane; x < NN; x += 32) H[x] = c.Hs[x];
     if (lane < N) {
         int* sk = a.streak + e * N + lane;
-        *sk = (used >> lane & 1u) ? 0 : *sk + 1;
+        *sk = (used >> lane & 1u) ? 0 : (a.fresh ? 0 : *sk) + 1;
     }
 }
 

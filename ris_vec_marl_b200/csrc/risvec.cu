@@ -952,8 +952,11 @@ static PairArgs pair_state_args(risvec_env* env) {
 }
 
 int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float* p01, int64_t p01_env_stride,
-                     int topk, double tau_q, int recalc_mask, const int32_t* reuse, int decay, void* stream) {
+                     int topk, double tau_q, int recalc_mask, const int32_t* reuse, int decay, int new_episode,
+                     void* stream) {
     if (!env || !cfg || !p01) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    if (new_episode && !recalc_mask)
+        return fail(RISVEC_ERR_INVALID, "new_episode needs recalc_mask (the first step of an episode builds the mask)");
     const int V = env->dims.V;
     if (V > RISVEC_PAIR_MAX_V)
         return fail(RISVEC_ERR_UNSUPPORTED, "pairing is an exact matching over 2^V subsets: V = %d > %d", V,
@@ -963,7 +966,7 @@ int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float
     CUDA_TRY(cudaSetDevice(env->device));
     PairArgs a = pair_state_args(env);
     a.p01 = p01; a.p01_stride = p01_env_stride; a.reuse = reuse;
-    a.topk = topk; a.tau_q = tau_q; a.recalc = recalc_mask != 0; a.decay = decay != 0;
+    a.topk = topk; a.tau_q = tau_q; a.recalc = recalc_mask != 0; a.decay = decay != 0; a.fresh = new_episode != 0;
     a.min_pairs = cfg->min_pair_target > 1 ? cfg->min_pair_target : 1;
     a.backoff_rounds = cfg->mwm_backoff_rounds;
     a.accept_q = cfg->mwm_accept_quantile; a.accept_q_step = cfg->mwm_accept_q_step;

@@ -81,11 +81,15 @@ def replay_gpu(g, device=0):
                              R_min_bpsHz=g["env"]["R_min"])
         env.set_pairing(**{k: v for k, v in g["cfg"].items() if not k.startswith("mask_")})
         env.gains.copy_(torch.as_tensor(g["gains"][idx], device=env.device))
-        env.pair_reset()
+        fold = (kq[0] + int(round(kq[1] * 1000))) % 2 == 1   # exercise both ways of starting an episode
+        if fold:     # stale state from a "previous episode" that new_episode=True must ignore
+            env.pair_hist.fill_(3.0); env.unpaired_streak.fill_(5); env.noma_ngroups.fill_(4)
+        else:
+            env.pair_reset()
         for t in range(T):
             p01 = torch.as_tensor(g["p01"][idx, t], device=env.device)
             reuse = torch.as_tensor(g["freeze"][idx, t], device=env.device)
-            env.pair_noma(p01, kq[0], kq[1], recalc_mask=(t == 0), reuse=reuse)
+            env.pair_noma(p01, kq[0], kq[1], recalc_mask=(t == 0), reuse=reuse, new_episode=(fold and t == 0))
             out["pairs"][idx, t] = env.noma_pairs.cpu().numpy()
             out["npairs"][idx, t] = env.noma_npairs.cpu().numpy()
             out["ngroups"][idx, t] = env.noma_ngroups.cpu().numpy()

@@ -113,7 +113,7 @@ def test_pairing_defaults_round_trip_through_the_struct(lib):
     assert (p.min_pair_target, p.mwm_backoff_rounds, p.abs_gain_min_db) == (3, 3, -120.0)
     assert lib.risvec_default_pairing(3, 0, C.byref(p)) == 0 and p.min_pair_target == 1
     assert lib.risvec_default_pairing(0, 0, C.byref(p)) == -1
-    assert lib.risvec_pair_noma(None, C.byref(p), None, 8, 7, 0.2, 1, None, 1, None) == -1
+    assert lib.risvec_pair_noma(None, C.byref(p), None, 8, 7, 0.2, 1, None, 1, 0, None) == -1
     assert lib.risvec_pair_reset(None, None) == -1
     src = open(os.path.join(ROOT, "include", "risvec.h")).read()
     assert int(re.search(r"#define RISVEC_PAIR_MAX_V (\d+)", src).group(1)) == _lib.PAIR_MAX_V

@@ -83,13 +83,11 @@ def main():
     def driver_step():
         first = ctr[0] % 100 == 0
         ctr[0] += 1
-        if first:
-            env.pair_reset()
         env.observe(out=obs)
         x = obs.to(torch.bfloat16) if a.actor_dtype == "bf16" else obs
         raw = actors(x).float()
         act = env.map_actions(raw)
-        part_v, ng_v = env.pair_noma(act, K, q, recalc_mask=first, reuse=None if first else frozen)
+        part_v, ng_v = env.pair_noma(act, K, q, recalc_mask=first, reuse=None if first else frozen, new_episode=first)
         probs = actors.intent(env.pair_mask)
         env.step_marl(act, part_v, ng_v)
         env.observe(out=obs2)

@@ -44,8 +44,7 @@ def main():
         env.update_channel_gains()
 
     def pairing():
-        env.pair_reset()
-        env.pair_noma(actions[0], K, q, recalc_mask=True)
+        env.pair_noma(actions[0], K, q, recalc_mask=True, new_episode=True)
 
     def steps():
         env.rollout_marl(actions, env.noma_partner, env.noma_ngroups, arrivals, out=out)

@@ -86,7 +86,7 @@ struct PairCtx {
     double rv[EPL];
     int rl[EPL], re[EPL], rn;
 
-    __device__ void rank_pass(const double* vals) {
+    __device__ void rank_pass(const double* vals, int len = NN) {   // entries >= len are invalid (+inf)
         int c = 0;
         for (int e = lane; e < NN; e += 32) c += valid[e] ? 1 : 0;
         rn = wsum(c);
@@ -99,7 +99,7 @@ struct PairCtx {
         }
         if (rn == 0) return;
 #pragma unroll 8
-        for (int o = 0; o < NN; ++o) {
+        for (int o = 0; o < len; ++o) {
             const double u = vals[o];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) {
@@ -136,26 +136,33 @@ struct PairCtx {
         return res;
     }
 
-    // _adaptive_threshold_from_delta_g (:842-855)
+    // _adaptive_threshold_from_delta_g (:842-855): quantile of |g_s - g_w| over strong x weak (the
+    // halves of the stable gain order); the nS * nW differences are stored compactly so that the
+    // counting pass runs over them only
     __device__ double adaptive_tau(double q) {
-        if (N < 2) return 0.0;
+        if constexpr (N < 2) {
+            return 0.0;
+        } else {
         if (lane < N) {
             int r = 0;
             const double v = g15[lane];
             for (int o = 0; o < N; ++o) r += (g15[o] < v || (g15[o] == v && o < lane)) ? 1 : 0;
-            wk[lane] = r < N / 2;
+            pr[r] = lane;       // pr is free here: vehicle at each rank
         }
         __syncwarp();
+        constexpr int nW = N / 2, nS = N - nW, n = nS * nW;
         for (int e = lane; e < NN; e += 32) {
-            const int i = e / N, j = e - i * N;
-            const bool ok = (!wk[i]) && wk[j];
+            const bool ok = e < n;
             valid[e] = ok;
-            W[e] = ok ? fabs(__dsub_rn(g15[i], g15[j])) : CUDART_INF;
+            W[e] = ok ? fabs(__dsub_rn(g15[pr[nW + e / nW]], g15[pr[e % nW]])) : CUDART_INF;
         }
         __syncwarp();
-        rank_pass(W);
+        rank_pass(W, n);
         s_ranked = false;
-        return rn ? select(q) : 0.0;
+        const double tau = rn ? select(q) : 0.0;
+        __syncwarp();
+        return tau;
+        }
     }
 
     // _build_feasible_mask_from_delta_g (:134-156) -> feas

@@ -166,10 +166,14 @@ def run_reference_arm(args, rank):
     # every "step" of this arm is a bounded sample of the same workload: `sample_s` seconds of
     # the per-env python loop on every host core
     per_step_s = max(1.0, min(10.0, 40.0 / max(1, args.steps + args.warmup)))
+    # at most 40 samples are actually run (~1 min), whatever K the caller asks for: the per-sample
+    # throughput of the CPU loop does not depend on how many samples are averaged
+    warm = min(args.warmup, 3)
+    n_run = warm + min(args.steps, 40 - warm)
     vals = []
-    for i in range(args.warmup + args.steps):
+    for i in range(n_run):
         v, n = cpu_port_throughput(args.workload, V, M, per_step_s, cores)
-        if i >= args.warmup:
+        if i >= warm:
             vals.append(v)
     value = sum(vals) / len(vals)
     line = {
@@ -179,7 +183,7 @@ def run_reference_arm(args, rank):
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"oracle/env_oracle.py per-env step loop (E=1 per process, reference loop shape), "
-                                   f"{cores} processes x {per_step_s:.1f} s per bench step"},
+                                   f"{cores} processes x {per_step_s:.1f} s per bench step, {len(vals)} timed samples"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -199,7 +203,7 @@ def workload_config(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sarl", choices=["sarl", "marl"])
@@ -314,9 +318,13 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        for _ in range(args.warmup):  # keep the GPU under load while nvidia-smi spins up
-            one_step()
-        torch.cuda.synchronize()
+        t_spin = time.time()
+        while True:  # keep the GPU under load until nvidia-smi delivers its first sample (<= 3 s)
+            for _ in range(max(args.warmup, 20)):
+                one_step()
+            torch.cuda.synchronize()
+            if sampler.lines or sampler.proc is None or time.time() - t_spin > 3.0:
+                break
         sampler.lines.clear()
     if world > 1:
         dist.barrier()

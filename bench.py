@@ -398,7 +398,8 @@ def main():
         peak, peak_src = measured_peak_gbs()
         if wl == "sarl":
             kernel_name = ("k_sarl_v8<%d,true,true,true> (packed records)" % (M // 8)) if packed else (
-                "k_sarl_v8" if (V <= 8 and M <= 40) else "k_sarl_rollout")
+                "k_sarl_v8" if (V <= 8 and M <= 40) else
+                ("k_sarl_rollout" if M <= 40 else "k_sarl_cascade2 + k_sarl_scan (timed together)"))
         else:
             kernel_name = "k_marl_v8<true,false>" if V <= 8 else "k_marl_rollout"
         alg = algorithmic_bytes(wl, V, M, T, E)

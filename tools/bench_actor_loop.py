@@ -59,9 +59,17 @@ def main():
     ap.add_argument("--replay-size", type=int, default=1_000_000)
     a = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = a.actor_dtype == "tf32"
-    dev = torch.device("cuda", 0)
+    # config 5 of BASELINE: under torchrun every rank steps its own shard of the envs (8192 per GPU x 8 =
+    # 65 536) with replicated actor weights; the only collective is the statistics all-reduce at the end
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
     E, V, M = a.envs, 8, 40
-    env = BatchedEnviron("marl", E, V, M, **marl_yaml_overrides())
+    env = BatchedEnviron("marl", E, V, M, device=local, seed=1234, env_index_base=rank * E, **marl_yaml_overrides())
     env.make_new_game(); env.renew_positions(); env.compute_parms(); env.optimize_phase_shift(); env.update_channel_gains()
     part, ng = encode_groups([[0, 1], [2, 3], [4, 5], [6], [7]], V)
     partner = torch.as_tensor(np.tile(part, (E, 1))).to(dev)
@@ -75,7 +83,7 @@ def main():
     if a.driver:
         env.set_pairing(yaml=True)
         env.pair_reset()
-        rb = ReplayBuffer(a.replay_size, 5, V + 2, V)
+        rb = ReplayBuffer(a.replay_size, 5, V + 2, V, device=local)
         K, q = mask_schedule(10, V, 7, 7, 0.10, 0.25, 200)
         frozen = torch.ones(E, dtype=torch.int32, device=dev)
         ctr = [0]
@@ -104,20 +112,25 @@ def main():
 
     def timed(fn, n):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(n):
             fn()
         t1.record()
         torch.cuda.synchronize()
-        return t0.elapsed_time(t1) * 1e-3
+        sec = torch.tensor([t0.elapsed_time(t1) * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)     # device-timed, max over ranks
+        return float(sec.item())
 
     for _ in range(5):
         step()
     res = {"config": {"envs": E, "V": V, "M": M, "steps": a.steps, "actor": "8 x MLP 5-512-256-2 (bmm), " + a.actor_dtype,
-                      "driver_loop": bool(a.driver)}}
+                      "driver_loop": bool(a.driver), "envs_per_gpu": E}}
     sec = timed(step, a.steps)
-    res["eager_env_steps_per_s"] = E * a.steps / sec
+    res["eager_env_steps_per_s"] = world * E * a.steps / sec
     res["eager_us_per_step"] = sec / a.steps * 1e6
     try:
         if a.driver:
@@ -130,15 +143,22 @@ def main():
             with torch.cuda.graph(g, stream=s):
                 step()
         sec = timed(g.replay, a.steps)
-        res["graph_env_steps_per_s"] = E * a.steps / sec
+        res["graph_env_steps_per_s"] = world * E * a.steps / sec
         res["graph_us_per_step"] = sec / a.steps * 1e6
     except Exception as exc:  # capture is best-effort
         res["graph_error"] = repr(exc)[:200]
     if a.driver:
         res["replay_rows"] = rb.mem_cntr
         res["pairs_mean"] = float(env.noma_npairs.float().mean())
-    res["mean_reward"] = float(env.reward.mean())
-    print(json.dumps(res))
+    stats = env.shard_stats()
+    if world > 1:
+        dist.all_reduce(stats)
+    res["n_gpus"] = world
+    res["mean_reward"] = float(stats[-1].item()) / (world * E)
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

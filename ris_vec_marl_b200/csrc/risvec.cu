@@ -165,7 +165,7 @@ int launch_sarl_cfg(risvec_env* env, const SarlArgs& a_in, cudaStream_t st) {
     while (chunk > 2 && (long long)blocks * ((a.T + chunk - 1) / chunk) < 4 * 148) chunk >>= 1;  // fill the SMs
     a.t_chunk = chunk;
     if constexpr (WPE > 1) {
-        const size_t smem2 = 12 * EPW * MS * sizeof(float) + 4 * WPE * 32 * sizeof(float2);
+        const size_t smem2 = 8 * EPW * MS * sizeof(float) + 4 * WPE * 32 * sizeof(float2);
         auto kern = k_sarl_cascade2<VP, MPL, WPE>;
         if (smem2 > 48 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

@@ -587,8 +587,8 @@ __global__ void __launch_bounds__(32 * WPE, (WPE <= 8 && MPL <= 32) ? 16 / WPE :
     const int E = d.E, V = d.V, M = d.M, T = a.T;
     const int MS = ((M + 4 * WPE + 7) / 4) * 4;
     const int plane = EPW * MS;
-    float* th = sarl_smem;                                               // [2 bufs][2 steps][3 planes][EPW][MS]
-    float2* part = reinterpret_cast<float2*>(sarl_smem + 12 * plane);    // [2 bufs][2 steps][WPE][32]
+    float* th = sarl_smem;                                               // [2 bufs][2 steps][2 planes][EPW][MS]
+    float2* part = reinterpret_cast<float2*>(sarl_smem + 8 * plane);     // [2 bufs][2 steps][WPE][32]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int el = lane / VP, v = lane % VP;
     const int e0 = blockIdx.x * EPW, e = e0 + el;
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(32 * WPE, (WPE <= 8 && MPL <= 32) ? 16 / WPE :
             wv = cmul64(wv, z);
         }
     }
-    for (int i = threadIdx.x; i < 12 * plane; i += NT) th[i] = 0.f;  // pad elements must stay finite
+    for (int i = threadIdx.x; i < 8 * plane; i += NT) th[i] = 0.f;  // pad elements must stay finite
     const int t_begin = (int)blockIdx.y * a.t_chunk, t_end = min(T, t_begin + a.t_chunk);
     const int n_ph = min(EPW, E - e0) * M;
     const size_t stepM = (size_t)E * M;
@@ -625,13 +625,13 @@ __global__ void __launch_bounds__(32 * WPE, (WPE <= 8 && MPL <= 32) ? 16 / WPE :
         pfb = (has0 && t + 1 < T) ? __ldg(r + stepM + threadIdx.x) : 0.f;
     };
     auto produce_pair = [&](int t, const float* r, int bufi) {  // theta of steps (t, t + 1) -> buffer bufi
-        float* b0 = th + bufi * 6 * plane;
-        float* b1 = b0 + 3 * plane;
+        float* b0 = th + bufi * 4 * plane;
+        float* b1 = b0 + 2 * plane;
         if (has0) {
             float2 sn, cs;
             sincos_fast2(make_float2(pfa, pfb), &sn, &cs);  // SARL:125-131
-            b0[off0] = cs.x; b0[plane + off0] = sn.x; b0[2 * plane + off0] = -sn.x;
-            b1[off0] = cs.y; b1[plane + off0] = sn.y; b1[2 * plane + off0] = -sn.y;
+            b0[off0] = cs.x; b0[plane + off0] = sn.x;
+            b1[off0] = cs.y; b1[plane + off0] = sn.y;
             if (t == T - 1) s.phase_real[(size_t)e0 * M + threadIdx.x] = pfa;
             if (t + 1 == T - 1) s.phase_real[(size_t)e0 * M + threadIdx.x] = pfb;
         }
@@ -640,8 +640,8 @@ __global__ void __launch_bounds__(32 * WPE, (WPE <= 8 && MPL <= 32) ? 16 / WPE :
             float2 sn, cs;
             sincos_fast2(make_float2(pa, pb), &sn, &cs);
             const int o = (idx / M) * MS + idx % M;
-            b0[o] = cs.x; b0[plane + o] = sn.x; b0[2 * plane + o] = -sn.x;
-            b1[o] = cs.y; b1[plane + o] = sn.y; b1[2 * plane + o] = -sn.y;
+            b0[o] = cs.x; b0[plane + o] = sn.x;
+            b1[o] = cs.y; b1[plane + o] = sn.y;
             if (t == T - 1) s.phase_real[(size_t)e0 * M + idx] = pa;
             if (t + 1 == T - 1) s.phase_real[(size_t)e0 * M + idx] = pb;
         }
@@ -661,20 +661,19 @@ __global__ void __launch_bounds__(32 * WPE, (WPE <= 8 && MPL <= 32) ? 16 / WPE :
         row += 2 * stepM;
         fetch_pair(row, t + 4);
 
-        const float* base = th + bufi * 6 * plane + el * MS + m0;
+        const float* base = th + bufi * 4 * plane + el * MS + m0;
         float2 RE[2][2], IM[2][2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) RE[u][0] = RE[u][1] = IM[u][0] = IM[u][1] = make_float2(0.f, 0.f);
         auto quad = [&](int gq) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const float4* c4 = reinterpret_cast<const float4*>(base + u * 3 * plane);
+                const float4* c4 = reinterpret_cast<const float4*>(base + u * 2 * plane);
                 const float4 tx = c4[gq];
-                const float4 ty = reinterpret_cast<const float4*>(base + u * 3 * plane + plane)[gq];
-                const float4 ny = reinterpret_cast<const float4*>(base + u * 3 * plane + 2 * plane)[gq];
+                const float4 ty = reinterpret_cast<const float4*>(base + u * 2 * plane + plane)[gq];
                 const float2 txa = make_float2(tx.x, tx.y), txb = make_float2(tx.z, tx.w);
                 const float2 tya = make_float2(ty.x, ty.y), tyb = make_float2(ty.z, ty.w);
-                const float2 nya = make_float2(ny.x, ny.y), nyb = make_float2(ny.z, ny.w);
+                const float2 nya = make_float2(-ty.x, -ty.y), nyb = make_float2(-ty.z, -ty.w);  // operand negation, no extra plane
                 RE[u][0] = __ffma2_rn(txa, WX[2 * gq], RE[u][0]); RE[u][0] = __ffma2_rn(nya, WY[2 * gq], RE[u][0]);
                 IM[u][0] = __ffma2_rn(txa, WY[2 * gq], IM[u][0]); IM[u][0] = __ffma2_rn(tya, WX[2 * gq], IM[u][0]);
                 RE[u][1] = __ffma2_rn(txb, WX[2 * gq + 1], RE[u][1]); RE[u][1] = __ffma2_rn(nyb, WY[2 * gq + 1], RE[u][1]);

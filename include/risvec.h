@@ -339,7 +339,8 @@ int risvec_replay_store_marl(risvec_replay_t* rb, int E, const float* state, con
                              const float* state_, const uint8_t* done, int done_all, const uint8_t* mask_u8,
                              void* stream);
 /* sample_buffer (buffer.py:27-39) for B caller-drawn slot indices idx [B] i64 (device), each in
- * [0, min(mem_cntr, mem_size)); outputs are [B, ...] device arrays shaped like the fields. */
+ * [0, min(mem_cntr, mem_size)) (indices outside [0, mem_size) are clamped); outputs are [B, ...]
+ * device arrays shaped like the fields. */
 int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* states, float* actions,
                          float* rewards_g, float* rewards_l, float* states_, uint8_t* dones, float* masks,
                          void* stream);

@@ -117,7 +117,7 @@ __global__ void k_replay_sample(ReplayMem m, int B, const long long* __restrict_
                                 unsigned char* __restrict__ dones, float* __restrict__ masks) {
     const int b = blockIdx.x;
     if (b >= B) return;
-    const long long slot = idx[b];
+    const long long slot = min(max(idx[b], 0LL), m.mem_size - 1);   // out-of-range indices are clamped, never read outside
     const int NN = m.N * m.N;
     for (int c = threadIdx.x; c < m.S; c += blockDim.x) {
         states[(size_t)b * m.S + c] = m.state[slot * m.S + c];

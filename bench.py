@@ -292,21 +292,24 @@ def main():
                 env.rollout_sarl(actions, phases, arrivals, out=out)
 
     pending = []
+    ring = torch.zeros(max(args.steps, args.warmup, 20) + 1, 17, dtype=torch.float64, device=dev) if world > 1 else None
 
     def episode_stats():
         # the only collective on the path: NCCL sum of a 17-entry f64 vector.  It is
-        # issued asynchronously (NCCL's own stream) so the next rollout overlaps it; `drain_stats`
-        # waits for all of them inside the timed region.
+        # issued asynchronously (NCCL's own stream) into a slot of a preallocated ring so the next
+        # rollout overlaps it; `drain_stats` waits for the last one (NCCL runs them in order) inside
+        # the timed region and folds the ring with one reduction.
         if world > 1:
-            sv = env.shard_stats()
-            pending.append((dist.all_reduce(sv, async_op=True), sv))
+            sv = ring[len(pending)]
+            env.shard_stats(out=sv)
+            pending.append(dist.all_reduce(sv, async_op=True))
         else:
             env.shard_stats(out=stats_sum, accumulate=True)
 
     def drain_stats():
-        for work, sv in pending:
-            work.wait()
-            stats_sum.add_(sv)
+        if pending:
+            pending[-1].wait()
+            stats_sum.add_(ring[:len(pending)].sum(0))
         pending.clear()
 
     for _ in range(args.warmup):

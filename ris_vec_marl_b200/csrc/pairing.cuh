@@ -86,10 +86,16 @@ struct PairCtx {
     double rv[EPL];
     int rl[EPL], re[EPL], rn;
 
-    __device__ void rank_pass(const double* vals, int len = NN) {   // entries >= len are invalid (+inf)
+    // `flag[e]` marks the valid entries (zero for e >= len, where vals holds +inf); `mul` is the
+    // multiplicity of every stored value (2 when only the upper triangle of a symmetric matrix is stored)
+    const unsigned char* rflag;
+    int rmul;
+    __device__ void rank_pass(const double* vals, int len, const unsigned char* flag, int mul) {
+        rflag = flag;
+        rmul = mul;
         int c = 0;
-        for (int e = lane; e < NN; e += 32) c += valid[e] ? 1 : 0;
-        rn = wsum(c);
+        for (int e = lane; e < NN; e += 32) c += flag[e] ? 1 : 0;
+        rn = wsum(c) * mul;
 #pragma unroll
         for (int k = 0; k < EPL; ++k) {
             const int e = lane + 32 * k;
@@ -107,6 +113,8 @@ struct PairCtx {
                 re[k] += u == rv[k];
             }
         }
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) { rl[k] *= mul; re[k] *= mul; }
     }
 
     // numpy.quantile(values of the last rank_pass, q, method="linear") incl. numpy's two-sided _lerp
@@ -122,7 +130,7 @@ struct PairCtx {
 #pragma unroll
         for (int k = 0; k < EPL; ++k) {
             const int e = lane + 32 * k;
-            if (e < NN && valid[e]) {   // equal values may be published by several lanes: same bits
+            if (e < NN && rflag[e]) {   // equal values may be published by several lanes: same bits
                 if (rl[k] <= lo && lo < rl[k] + re[k]) slot[0] = rv[k];
                 if (rl[k] <= hi && hi < rl[k] + re[k]) slot[1] = rv[k];
             }
@@ -157,7 +165,7 @@ struct PairCtx {
             W[e] = ok ? fabs(__dsub_rn(g15[pr[nW + e / nW]], g15[pr[e % nW]])) : CUDART_INF;
         }
         __syncwarp();
-        rank_pass(W, n);
+        rank_pass(W, n, valid, 1);
         s_ranked = false;
         const double tau = rn ? select(q) : 0.0;
         __syncwarp();
@@ -272,13 +280,36 @@ struct PairCtx {
     bool s_ranked;
     __device__ void rank_edges() {
         if (s_ranked) return;
+        bool sym = true;
         for (int e = lane; e < NN; e += 32) {
+            const int i = e / N, j = e - i * N;
             const bool ok = isfinite(S[e]);
             valid[e] = ok;
-            W[e] = ok ? S[e] : CUDART_INF;    // +inf in place of the non-edges: the layout rank_pass wants
+            sym = sym && (S[e] == S[j * N + i]);          // -inf == -inf; S holds no NaN
         }
+        sym = __all_sync(kFull, sym);
         __syncwarp();
-        rank_pass(W);
+        if (sym && N >= 2) {
+            // symmetric scores (always, unless a back-off round or an exact gain tie broke it): every
+            // value occurs twice, so the counting pass runs over the N (N - 1) / 2 upper-triangle values
+            constexpr int NT = N * (N - 1) / 2;
+            for (int e = lane; e < NN; e += 32) { tmp[e] = 0; W[e] = CUDART_INF; }
+            __syncwarp();
+            for (int e = lane; e < NN; e += 32) {
+                const int i = e / N, j = e - i * N;
+                if (i < j) {
+                    const int t = i * N - (i * (i + 1)) / 2 + (j - i - 1);
+                    tmp[t] = valid[e];
+                    W[t] = valid[e] ? S[e] : CUDART_INF;
+                }
+            }
+            __syncwarp();
+            rank_pass(W, NT, tmp, 2);
+        } else {
+            for (int e = lane; e < NN; e += 32) W[e] = valid[e] ? S[e] : CUDART_INF;   // the layout rank_pass wants
+            __syncwarp();
+            rank_pass(W, NN, valid, 1);
+        }
         __syncwarp();
         s_ranked = true;
     }

@@ -2,6 +2,7 @@
 
     python -m ris_vec_marl_b200.compat.run_driver marl /path/to/reference [driver args...]
     python -m ris_vec_marl_b200.compat.run_driver sarl /path/to/reference
+    python -m ris_vec_marl_b200.compat.run_driver marl_test /path/to/reference
 
 The driver .py files and config.yaml are copied to a scratch directory (the reference
 creates checkpoint directories next to its modules), the scratch dir
@@ -14,7 +15,9 @@ import sys
 import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DRIVERS = {"marl": ("Simulation-MARL-BCD", "marl_train_bcd.py"), "sarl": ("Simulation-SARL", "ddpg_train.py")}
+DRIVERS = {"marl": ("Simulation-MARL-BCD", "marl_train_bcd.py"), "sarl": ("Simulation-SARL", "ddpg_train.py"),
+           # the stale MADDPG test script: compat/marl also provides its missing `ddpg_torch` / `global_critic`
+           "marl_test": ("Simulation-MARL-BCD", "marl_test.py")}
 
 
 def main(argv):
@@ -28,7 +31,10 @@ def main(argv):
         if f.endswith((".py", ".yaml")) and f != "Environment.py":
             shutil.copy(os.path.join(src, f), scratch)
     os.chdir(scratch)
-    sys.path[:0] = [os.path.join(HERE, variant), os.path.join(HERE, "stubs"), scratch]
+    compat_dir = "marl" if variant == "marl_test" else variant
+    if variant == "marl_test":  # shipped MADDPG checkpoints stay where they are (read-only)
+        os.environ.setdefault("RISVEC_MARL_MODEL_DIR", os.path.join(src, "model2", "3-BCD_RIS_marl_ddpg-8"))
+    sys.path[:0] = [os.path.join(HERE, compat_dir), os.path.join(HERE, "stubs"), scratch]
     sys.argv = [script] + rest
     runpy.run_path(os.path.join(scratch, script), run_name="__main__")
 

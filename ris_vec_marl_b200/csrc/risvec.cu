@@ -1136,7 +1136,8 @@ int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* str
     if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(env->device));
     if (!accumulate) CUDA_TRY(cudaMemsetAsync(out, 0, (RISVEC_NSTAT + 1) * sizeof(double), (cudaStream_t)stream));
-    const int blocks = env->dims.E >= 1024 ? 16 : (env->dims.E + 63) / 64;
+    int blocks = (env->dims.E + 63) / 64;   // 64 envs per block and pass; at most one block per SM
+    if (blocks > 148) blocks = 148;
     k_shard_stats<<<blocks, 1024, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
     return check_launch(env, "k_shard_stats");
 }

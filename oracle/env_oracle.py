@@ -711,6 +711,7 @@ class EnvOracle:
         self.data_p = np.power(a[:, 1, :] / p.k, 1.0 / 3.0) * p.time_fast / p.L / 1000  # :331
 
         buf = self.DataBuf - (self.data_t + self.data_p)
+        buf_signed = buf.copy()  # pre-clamp value: the sign decides the reward penalties (:334-352)
         neg = buf < 0
         b_arg = np.fmax(0, buf + self.data_p)
         rev = np.power(b_arg * 1000 * p.L / p.time_fast, 3.0) * p.k  # :318-319
@@ -726,5 +727,5 @@ class EnvOracle:
         self.data_r = np.asarray(arr, dtype=float)
         self.DataBuf = self.DataBuf + self.data_r * p.time_fast * 1000
         reward = _rowmean(per_user)
-        self.last = dict(per_user_reward=per_user, gain=gain)
+        self.last = dict(per_user_reward=per_user, gain=gain, buf_signed=buf_signed)
         return reward, over_power

@@ -15,7 +15,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("RISVEC_LIB") or os.path.join(PKG_DIR, "librisvec.so")  # override: A/B builds
 SOURCES = ["risvec.cu"]
-HEADERS = ["common.cuh", "geom.cuh", "ris.cuh", "step.cuh", "pairing.cuh", "replay.cuh"]
+HEADERS = ["common.cuh", "geom.cuh", "ris.cuh", "step.cuh", "sarl_mma.cuh", "pairing.cuh", "replay.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 
@@ -155,6 +155,7 @@ EXPORTS = {
     "risvec_replay_sample": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_void_p]),
     "risvec_shard_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "risvec_launch_count": (C.c_int64, [C.c_void_p]),
+    "risvec_last_step_kernel": (C.c_char_p, [C.c_void_p]),
 }
 
 

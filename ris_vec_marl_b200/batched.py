@@ -184,6 +184,10 @@ class BatchedEnviron:
     def launch_count(self):
         return int(self._lib.risvec_launch_count(self._h))
 
+    def last_kernel(self):
+        """Name of the kernel(s) the latest rollout / step call launched (`risvec_last_step_kernel`)."""
+        return self._lib.risvec_last_step_kernel(self._h).decode()
+
     # ------------------------------------------------------------------ reference methods
     def make_new_game(self, reset_ints=None, reset_dirs=None):
         ri = self._dev(reset_ints, torch.int32)

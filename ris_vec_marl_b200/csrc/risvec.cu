@@ -10,6 +10,7 @@
 #include "geom.cuh"
 #include "ris.cuh"
 #include "step.cuh"
+#include "sarl_mma.cuh"
 #include "pairing.cuh"
 #include "replay.cuh"
 
@@ -67,6 +68,8 @@ struct risvec_env {
     cudaStream_t s_in, s_out;
     cudaEvent_t ev[2 * 64 + 2];  // 2 * kMaxChunks + 2
     int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
+    int sarl_path;      // RISVEC_SARL_PATH = auto (0) | mma (1) | v8 (2) | generic (3): tests / A-B runs
+    const char* step_kernel;  // name of the kernel(s) the latest rollout launched (risvec_last_step_kernel)
 };
 
 struct risvec_replay {
@@ -84,6 +87,11 @@ int check_launch(risvec_env* env, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RISVEC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     env->launches += 1;
+    return RISVEC_OK;
+}
+int check_step_launch(risvec_env* env, const char* what) {  // a rollout kernel: remember which one ran
+    if (int rc = check_launch(env, what)) return rc;
+    env->step_kernel = what;
     return RISVEC_OK;
 }
 
@@ -130,7 +138,7 @@ int launch_marl(risvec_env* env, const MarlArgs& a, cudaStream_t st) {
     const long long total = (long long)env->dims.E * VP;
     const int blocks = (int)((total + threads - 1) / threads);
     k_marl_rollout<VP><<<blocks, threads, 0, st>>>(env->dims, env->st, env->params, a);
-    return check_launch(env, "k_marl_rollout");
+    return check_step_launch(env, "k_marl_rollout");
 }
 
 int ensure_scratch(risvec_env* env, size_t bytes) {
@@ -155,7 +163,7 @@ int launch_sarl_cfg(risvec_env* env, const SarlArgs& a_in, cudaStream_t st) {
         auto kern = k_sarl_rollout<VP, MPL, WPE>;
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, 32 * WPE, smem, st>>>(env->dims, env->st, env->params, a);
-        return check_launch(env, "k_sarl_rollout");
+        return check_step_launch(env, "k_sarl_rollout");
     }
     // several warps per env (large M): cascade kernel over (env group, time chunk) -> |S|^2 scratch,
     // then the per-vehicle scan kernel
@@ -174,7 +182,9 @@ int launch_sarl_cfg(risvec_env* env, const SarlArgs& a_in, cudaStream_t st) {
     }
     const long long total = (long long)E * VP;
     k_sarl_scan<VP><<<(int)((total + 127) / 128), 128, 0, st>>>(env->dims, env->st, env->params, a);
-    return check_launch(env, "k_sarl_scan");
+    if (int rc = check_launch(env, "k_sarl_scan")) return rc;
+    env->step_kernel = "k_sarl_cascade2+k_sarl_scan";
+    return RISVEC_OK;
 }
 
 template <int MPI>
@@ -192,13 +202,39 @@ int launch_sarl_v8(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
         k_sarl_v8<MPI, true, false, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
     else
         k_sarl_v8<MPI, false, false, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
-    return check_launch(env, "k_sarl_v8");
+    return check_step_launch(env, "k_sarl_v8");
+}
+
+// tensor-core path (sarl_mma.cuh): one warp per env, 4 envs per block; V <= 8, M even, M <= 8 KT
+template <int KT>
+int launch_sarl_mma(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
+    const int blocks = (env->dims.E + 3) / 4;
+    const risvec_sarl_out_t& o = a.out;
+    const bool full = env->dims.V == 8 && env->dims.M == 8 * KT && a.arrivals && o.reward && o.DataBuf && o.data_t &&
+                      o.data_p && o.over_power && o.over_data && o.rate;
+    if (full)
+        k_sarl_mma<KT, true><<<blocks, 128, 0, st>>>(env->dims, env->st, env->params, a);
+    else
+        k_sarl_mma<KT, false><<<blocks, 128, 0, st>>>(env->dims, env->st, env->params, a);
+    return check_step_launch(env, "k_sarl_mma");
+}
+inline bool sarl_mma_covers(const risvec_env* env) {
+    return env->dims.V <= 8 && env->dims.M % 2 == 0 && env->dims.M <= 64;
 }
 
 template <int VP>
 int launch_sarl(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     const int M = env->dims.M;
-    if (VP <= 8 && M <= 40 && !env->force_generic)  // fast path: elements split over the env's 8 lanes
+    enum { kAuto = 0, kMma = 1, kV8 = 2, kGeneric = 3 };
+    const int path = env->force_generic ? kGeneric : env->sarl_path;
+    if (VP <= 8 && sarl_mma_covers(env) && a.in_rec == nullptr && (path == kAuto || path == kMma)) {
+        if (M <= 8) return launch_sarl_mma<1>(env, a, st);
+        if (M <= 16) return launch_sarl_mma<2>(env, a, st);
+        if (M <= 24) return launch_sarl_mma<3>(env, a, st);
+        if (M <= 40) return launch_sarl_mma<5>(env, a, st);
+        return launch_sarl_mma<8>(env, a, st);
+    }
+    if (VP <= 8 && M <= 40 && path != kGeneric)  // elements split over the env's 8 lanes (FP32 pipe)
         return M <= 16 ? launch_sarl_v8<2>(env, a, st) : launch_sarl_v8<5>(env, a, st);
     // elements per lane: M / WPE, register-resident table of MPL complex floats
     if (M <= 16) return launch_sarl_cfg<VP, 16, 1>(env, a, st);
@@ -315,6 +351,9 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
     {
         const char* fg = getenv("RISVEC_FORCE_GENERIC");
         env->force_generic = (fg != nullptr && fg[0] == '1');
+        const char* sp = getenv("RISVEC_SARL_PATH");
+        env->sarl_path = !sp ? 0 : (!strcmp(sp, "mma") ? 1 : (!strcmp(sp, "v8") ? 2 : (!strcmp(sp, "generic") ? 3 : 0)));
+        env->step_kernel = "";
     }
     Dims& d = env->dims;
     d.E = E; d.V = V; d.M = M; d.ncand = 1 << control_bit; d.variant = variant;
@@ -527,7 +566,7 @@ int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int
             k_marl_v8<true, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
         else
             k_marl_v8<false, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);
-        return check_launch(env, "k_marl_v8");
+        return check_step_launch(env, "k_marl_v8");
     }
     switch (pow2ceil(env->dims.V)) {
         case 1: return launch_marl<1>(env, a, st);
@@ -602,7 +641,7 @@ int risvec_rollout_marl_packed(risvec_env_t* env, int T, const void* in_rec, con
     a.out.reward = reward;
     const int warps = (env->dims.E + 3) / 4;
     k_marl_v8<true, true><<<warps, 32, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, a);
-    return check_launch(env, "k_marl_v8");
+    return check_step_launch(env, "k_marl_v8");
 }
 
 // ---- host-buffer variants.  The T steps are cut into chunks and pipelined over three streams:
@@ -1143,5 +1182,6 @@ int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* str
 }
 
 int64_t risvec_launch_count(const risvec_env_t* env) { return env ? env->launches : 0; }
+const char* risvec_last_step_kernel(const risvec_env_t* env) { return (env && env->step_kernel) ? env->step_kernel : ""; }
 
 }  // extern "C"

@@ -13,6 +13,28 @@ def np64(t):
 FAST_MARL_TRACES = ("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate")
 
 
+class sarl_path:
+    """`with sarl_path("v8"): env = BatchedEnviron("sarl", ...)` pins the SARL rollout kernel of the handles
+    created inside (RISVEC_SARL_PATH = auto | mma | v8 | generic is read by risvec_create)."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def __enter__(self):
+        import os
+
+        self.old = os.environ.get("RISVEC_SARL_PATH")
+        os.environ["RISVEC_SARL_PATH"] = self.path
+
+    def __exit__(self, *exc):
+        import os
+
+        if self.old is None:
+            os.environ.pop("RISVEC_SARL_PATH", None)
+        else:
+            os.environ["RISVEC_SARL_PATH"] = self.old
+
+
 class GpuBackend:
     """mode="fast": the shape-specialised kernels where they apply (k_sarl_v8 / k_marl_v8; the MARL
     one takes `last_*`, `last_power_W`, `over_power` from the state views, as the compat layer

@@ -93,7 +93,7 @@ class OracleBackend:
         r, over_p = self.env.step_sarl(actions, phases)
         e = self.env
         return dict(reward=r, DataBuf=e.DataBuf, data_t=e.data_t, data_p=e.data_p, over_power=over_p,
-                    over_data=e.over_data, rate=e.vehicle_rate, x_buf_pre=e.DataBuf - e.data_r)
+                    over_data=e.over_data, rate=e.vehicle_rate, x_buf_signed=e.last["buf_signed"])
 
 
 def replay(g, backend):

@@ -212,6 +212,7 @@ def test_packed_records_are_bit_identical_to_per_array_api():
     """The packed record entry points (device and pinned-host pipelines) against the per-array
     ones: same kernels' arithmetic, so every trace and the final state must match bit for bit."""
     from ris_vec_marl_b200 import BatchedEnviron, RisvecError, encode_groups, marl_yaml_overrides
+    from tests.gpu_backend import sarl_path
 
     E, V, M, T = 1028, 8, 40, 37  # odd T; E % 4 == 0 as the tiled layout requires
     gen = torch.Generator().manual_seed(21)
@@ -220,7 +221,8 @@ def test_packed_records_are_bit_identical_to_per_array_api():
     arr = torch.poisson(torch.full((T, E, V), 2.0), generator=gen).to(torch.int32)
     for variant in ("sarl", "marl"):
         over = marl_yaml_overrides() if variant == "marl" else {}
-        envs = [BatchedEnviron(variant, E, V, M, seed=5, **over) for _ in range(3)]
+        with sarl_path("v8"):  # the packed SARL records run k_sarl_v8: compare with the same kernel's per-array form
+            envs = [BatchedEnviron(variant, E, V, M, seed=5, **over) for _ in range(3)]
         for e in envs:
             e.make_new_game(); e.renew_positions(); e.compute_parms()
             if variant == "marl":

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle.env_oracle import EnvOracle, InjectedDraws, OracleParams, encode_groups
-from tests.parity import RTOL, sarl_rate_atol
+from tests.parity import RTOL, sarl_rate_atol, sarl_reward_band
 
 pytestmark = pytest.mark.gpu
 
@@ -47,14 +47,16 @@ def test_sarl_random_shapes(V, M):
     o.make_new_game(); d.set_mobility_uniforms(mob); o.renew_positions(); o.compute_parms()
     assert np.array_equal(env.pos_x.cpu().numpy(), o.pos[..., 0]) and np.array_equal(env.dir.cpu().numpy(), o.dir)
     ra = sarl_rate_atol(M)
+    n_band = 0
     for t in range(T):
         rew, over_p = o.step_sarl(acts[t], phs[t])
-        pre = o.DataBuf - o.data_r
-        band = ((np.abs(pre) < 4 * ra) | (np.abs(o.over_data - 2.0) < 4 * ra)).any(axis=1)
+        band = sarl_reward_band(o.last["buf_signed"], o.over_data, M).any(axis=1)
+        n_band += int(band.sum())
         close(got["rate"][t], o.vehicle_rate, ra, f"rate t={t}")
         close(got["DataBuf"][t], o.DataBuf, 4 * ra, f"DataBuf t={t}")
         close(got["over_power"][t], over_p, 4e-6 + 4 * ra, f"over_power t={t}")
         close(got["reward"][t][~band], rew[~band], 4e-6 + ra, f"reward t={t}")
+    assert n_band <= 0.05 * E * T + 1, f"{n_band} of {E * T} env-steps band-excluded from the reward check"
 
 
 @pytest.mark.parametrize("V,M", [(1, 3), (2, 5), (7, 12), (13, 40), (24, 9), (32, 64)])

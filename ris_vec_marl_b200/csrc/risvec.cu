@@ -69,6 +69,7 @@ struct risvec_env {
     cudaEvent_t ev[2 * 64 + 2];  // 2 * kMaxChunks + 2
     int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
     int sarl_path;      // RISVEC_SARL_PATH = auto (0) | mma (1) | v8 (2) | generic (3): tests / A-B runs
+    int sarl_tma;       // RISVEC_SARL_TMA = 0 keeps the mma path on its LDG kernel (tests / A-B runs)
     const char* step_kernel;  // name of the kernel(s) the latest rollout launched (risvec_last_step_kernel)
 };
 
@@ -212,11 +213,71 @@ int launch_sarl_mma(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     const risvec_sarl_out_t& o = a.out;
     const bool full = env->dims.V == 8 && env->dims.M == 8 * KT && a.arrivals && o.reward && o.DataBuf && o.data_t &&
                       o.data_p && o.over_power && o.over_data && o.rate;
-    if (full)
-        k_sarl_mma<KT, true><<<blocks, 128, 0, st>>>(env->dims, env->st, env->params, a);
-    else
-        k_sarl_mma<KT, false><<<blocks, 128, 0, st>>>(env->dims, env->st, env->params, a);
+    (void)full;  // the fully-specified BASELINE shape normally runs k_sarl_mma_tma; this is the generic form
+    k_sarl_mma<KT, false><<<blocks, 128, 0, st>>>(env->dims, env->st, env->params, a);
     return check_step_launch(env, "k_sarl_mma");
+}
+// ---- TMA-staged variant (k_sarl_mma_tma): 2-D tensor maps over the caller's arrays, encoded per call
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {  // cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// rows x inner 4-byte elements, dense; box = box_rows x box_inner
+bool tensor_map_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t rows,
+                   uint32_t box_inner, uint32_t box_rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {inner, rows}, strides[1] = {inner * 4};
+    const cuuint32_t box[2] = {box_inner, box_rows}, estr[2] = {1, 1};
+    return enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+           CUDA_SUCCESS;
+}
+
+constexpr int kSarlTmaStages = 3;
+template <int KT>
+int launch_sarl_mma_tma(risvec_env* env, const SarlArgs& a, cudaStream_t st, bool* launched) {
+    *launched = false;
+    const int E = env->dims.E, V = env->dims.V, M = env->dims.M, T = a.T;
+    CUtensorMap tm_ph, tm_ac, tm_ar;
+    if (!tensor_map_2d(&tm_ph, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.phase, (uint64_t)E * M, T, M, kSarlTmaRows) ||
+        !tensor_map_2d(&tm_ac, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.action, (uint64_t)E * 2 * V, T, 2 * V, kSarlTmaRows) ||
+        !tensor_map_2d(&tm_ar, CU_TENSOR_MAP_DATA_TYPE_INT32, a.arrivals, (uint64_t)E * V, T, V, kSarlTmaRows))
+        return RISVEC_OK;  // not encodable here: the caller falls back to the LDG kernel
+    auto kern = k_sarl_mma_tma<KT, kSarlTmaStages>;
+    const int smem = 4 * kSarlTmaStages * sarl_tma_stage_bytes(KT) + 4 * kSarlTmaStages * 8 + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    kern<<<(E + 3) / 4, 128, smem, st>>>(env->dims, env->st, env->params, a, tm_ph, tm_ac, tm_ar);
+    *launched = true;
+    return check_step_launch(env, "k_sarl_mma_tma");
+}
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+// the TMA kernel covers the BASELINE shape: V = 8, M = 16 or 40, every trace + the arrivals supplied,
+// 16-byte aligned streams, 32-bit element indices
+inline bool sarl_tma_covers(const risvec_env* env, const SarlArgs& a) {
+    const risvec_sarl_out_t& o = a.out;
+    const int M = env->dims.M;
+    return env->dims.V == 8 && (M == 16 || M == 40) && a.arrivals && o.reward && o.DataBuf && o.data_t && o.data_p &&
+           o.over_power && o.over_data && o.rate && aligned16(a.phase) && aligned16(a.action) && aligned16(a.arrivals) &&
+           (uint64_t)a.T * env->dims.E * (M > 16 ? M : 16) < (1ull << 31);
 }
 inline bool sarl_mma_covers(const risvec_env* env) {
     return env->dims.V <= 8 && env->dims.M % 2 == 0 && env->dims.M <= 64;
@@ -228,6 +289,11 @@ int launch_sarl(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     enum { kAuto = 0, kMma = 1, kV8 = 2, kGeneric = 3 };
     const int path = env->force_generic ? kGeneric : env->sarl_path;
     if (VP <= 8 && sarl_mma_covers(env) && a.in_rec == nullptr && (path == kAuto || path == kMma)) {
+        if (sarl_tma_covers(env, a) && env->sarl_tma) {
+            bool launched = false;
+            const int rc = M == 16 ? launch_sarl_mma_tma<2>(env, a, st, &launched) : launch_sarl_mma_tma<5>(env, a, st, &launched);
+            if (rc != RISVEC_OK || launched) return rc;
+        }
         if (M <= 8) return launch_sarl_mma<1>(env, a, st);
         if (M <= 16) return launch_sarl_mma<2>(env, a, st);
         if (M <= 24) return launch_sarl_mma<3>(env, a, st);
@@ -354,6 +420,12 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
         const char* sp = getenv("RISVEC_SARL_PATH");
         env->sarl_path = !sp ? 0 : (!strcmp(sp, "mma") ? 1 : (!strcmp(sp, "v8") ? 2 : (!strcmp(sp, "generic") ? 3 : 0)));
         env->step_kernel = "";
+        const char* tm = getenv("RISVEC_SARL_TMA");
+        env->sarl_tma = !(tm != nullptr && tm[0] == '0');
+        if (sp && !strcmp(sp, "mma-ldg")) {  // the tensor-core path without the TMA staging
+            env->sarl_path = 1;
+            env->sarl_tma = 0;
+        }
     }
     Dims& d = env->dims;
     d.E = E; d.V = V; d.M = M; d.ncand = 1 << control_bit; d.variant = variant;

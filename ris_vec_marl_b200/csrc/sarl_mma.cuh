@@ -23,6 +23,7 @@
 // the four lanes that hold one vehicle's eight steps pass DataBuf along by shuffles, so results do
 // not depend on where a rollout is cut into launches or tiles.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved at run time)
 #include <cuda_fp16.h>
 
 #include "step.cuh"
@@ -262,6 +263,286 @@ __global__ void __launch_bounds__(128, 4) k_sarl_mma(Dims d, State s, risvec_par
             s.step_ctr[e] = step0 + T;
         }
     }
+}
+
+// =========================================================================================
+// The same rollout with TMA-staged inputs: the BASELINE shape (V = 8, M = 8 KT, every trace written)
+// =========================================================================================
+// What k_sarl_mma above still pays for is addressing and exposed load latency: its prefetched LDGs share
+// the warp's six scoreboard slots with the MUFU / shuffle / float64 traffic of the step, so the loads are
+// waited for long before their data is needed.  Here every warp owns a ring of shared-memory stages and
+// one lane per warp issues, per 16 steps, three cp.async.bulk.tensor copies (the env's rows of phase
+// [T, E*M], action [T, E*16] and arrivals [T, E*8], as 2-D tensor maps with boxes {M,16}, {16,16}, {8,16})
+// that complete on the stage's mbarrier: loads cost no issue slots, no registers and no scoreboard, and
+// run two stages ahead.  A stage is processed as two independent 8-step mma tiles (shared A fragments,
+// interleaved instruction streams).  The DataBuf recursion x -> max(x - d, 0) + inc is a max-plus affine
+// map, so the four lanes of a vehicle combine their two-step maps with a 2-round shuffle scan (float64)
+// and then redo their own two steps sequentially from the resulting start value; across launches the
+// results are reproducible for the same tiling (tiles start at the launch's first step).
+// Index arithmetic is 32-bit (the host checks T*E*M < 2^32).  Rows past T (last, partial stage) are
+// zero-filled by TMA and act as identity steps.
+
+// sin/cos of two float32 angles, packed fp32x2: k = rint(x / pi), r = x - k*pi in [-pi/2, pi/2]
+// (Cody-Waite, two terms), minimax polynomials of degree 9 / 10 on that interval (fitted for this file:
+// |error| <= 1.5e-7 absolute, 2-3e-8 rms on [0, 2 pi] in float32 arithmetic), sign (-1)^k on both --
+// no quadrant swap, so the fix-up is one shift and two XORs per angle.
+__device__ __forceinline__ void sincos_pi2(float2 x, float2* sn, float2* cs) {
+    const float2 t = __ffma2_rn(x, f2(0.318309886183790672f), f2(12582912.f));  // 1.5 * 2^23: rint
+    const float2 kf = __fadd2_rn(t, f2(-12582912.f));
+    float2 r = __ffma2_rn(kf, f2(-3.1415927410125732f), x);
+    r = __ffma2_rn(kf, f2(8.742277657347586e-8f), r);
+    const float2 r2 = __fmul2_rn(r, r);
+    float2 ps = __ffma2_rn(r2, f2(2.599751496745739e-06f), f2(-0.00019806479394901544f));
+    ps = __ffma2_rn(ps, r2, f2(0.008333015255630016f));
+    ps = __ffma2_rn(ps, r2, f2(-0.16666656732559204f));
+    const float2 s0 = __ffma2_rn(__fmul2_rn(ps, r2), r, r);
+    float2 pc = __ffma2_rn(r2, f2(-2.607421833999979e-07f), f2(2.4761729946476407e-05f));
+    pc = __ffma2_rn(pc, r2, f2(-0.0013888400280848145f));
+    pc = __ffma2_rn(pc, r2, f2(0.04166664183139801f));
+    pc = __ffma2_rn(pc, r2, f2(-0.5f));
+    const float2 c0 = __ffma2_rn(pc, r2, f2(1.0f));
+    const int sa = __float_as_int(t.x) << 31, sb = __float_as_int(t.y) << 31;  // parity of k
+    sn->x = __int_as_float(__float_as_int(s0.x) ^ sa);
+    cs->x = __int_as_float(__float_as_int(c0.x) ^ sa);
+    sn->y = __int_as_float(__float_as_int(s0.y) ^ sb);
+    cs->y = __int_as_float(__float_as_int(c0.y) ^ sb);
+}
+
+// ---- mbarrier / TMA primitives (PTX; SASS: SYNCS.*, UTMALDG)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// max-plus affine map x -> max(x + a, b): the DataBuf step x -> max(x - d, 0) + inc is (inc - d, inc)
+struct MaxPlus {
+    double a, b;
+};
+__device__ __forceinline__ MaxPlus mp_then(const MaxPlus& f, const MaxPlus& g) {  // g after f
+    MaxPlus r;
+    r.a = f.a + g.a;
+    const double fb = f.b + g.a;
+    r.b = fb > g.b ? fb : g.b;
+    return r;
+}
+__device__ __forceinline__ double mp_apply(const MaxPlus& f, double x) {
+    const double y = x + f.a;
+    return y > f.b ? y : f.b;
+}
+
+constexpr int kSarlTmaRows = 16;  // steps per stage (two 8-step mma tiles)
+__host__ __device__ constexpr int sarl_tma_stage_bytes(int KT) { return kSarlTmaRows * (8 * KT + 16 + 8) * 4; }
+
+template <int KT, int STAGES>
+__global__ void __launch_bounds__(128, 4)
+    k_sarl_mma_tma(Dims d, State s, risvec_params_t p, SarlArgs a, const __grid_constant__ CUtensorMap tm_ph,
+                   const __grid_constant__ CUtensorMap tm_ac, const __grid_constant__ CUtensorMap tm_ar) {
+    constexpr int M = 8 * KT, V = 8, R = kSarlTmaRows;
+    constexpr int PH_BYTES = R * M * 4, AC_BYTES = R * 2 * V * 4, AR_BYTES = R * V * 4;
+    constexpr int STAGE_BYTES = PH_BYTES + AC_BYTES + AR_BYTES;
+    static_assert(STAGE_BYTES == sarl_tma_stage_bytes(KT) && STAGE_BYTES % 128 == 0, "");
+    extern __shared__ unsigned char sarl_tma_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    const int E = d.E, T = a.T;
+    const int e = blockIdx.x * 4 + warp;
+    if (e >= E) return;  // warps are independent: no block-level synchronisation below
+
+    // ---- this warp's stage ring + its mbarriers (128 B aligned for the TMA destinations)
+    const uint32_t smem0 = (smem_u32(sarl_tma_smem_raw) + 127u) & ~127u;
+    const uint32_t ring = smem0 + (uint32_t)warp * (STAGES * STAGE_BYTES);
+    const uint32_t bars = smem0 + 4u * (STAGES * STAGE_BYTES) + (uint32_t)warp * (STAGES * 8);
+    const unsigned char* ring_g = sarl_tma_smem_raw + (smem0 - smem_u32(sarl_tma_smem_raw)) + warp * (STAGES * STAGE_BYTES);
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES; ++st) mbar_init(bars + 8 * st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    const int NS = (T + R - 1) / R;  // stages of 16 steps in this rollout
+    auto issue = [&](int k) {       // lane 0: the env's rows of steps [16 k, 16 k + 16) -> stage k % STAGES
+        const uint32_t dst = ring + (uint32_t)(k % STAGES) * STAGE_BYTES, bar = bars + 8 * (k % STAGES);
+        mbar_expect_tx(bar, STAGE_BYTES);
+        tma_load_2d(dst, &tm_ph, e * M, k * R, bar);
+        tma_load_2d(dst + PH_BYTES, &tm_ac, e * 2 * V, k * R, bar);
+        tma_load_2d(dst + PH_BYTES + AC_BYTES, &tm_ar, e * V, k * R, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < STAGES - 1; ++k)
+            if (k < NS) issue(k);
+    }
+
+    // ---- A operand (see k_sarl_mma): phasors of vehicle g at elements 8 j + 2 tig + {0, 1}
+    const size_t ev = (size_t)e * V + g;
+    uint32_t Ah[KT][4], Al[KT][4];
+    {
+        const double2 z = unit_phasor64(d.angle_BR - s.angle[ev]);
+        const double2 z2 = cmul64(z, z), z4 = cmul64(z2, z2), z8 = cmul64(z4, z4);
+        double2 w = cpow64(z, 2u * (unsigned)tig);
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            const double2 wb = cmul64(w, z);
+            split_h2(w.x, -w.y, Ah[j][0], Al[j][0]);
+            split_h2(w.y, w.x, Ah[j][1], Al[j][1]);
+            split_h2(wb.x, -wb.y, Ah[j][2], Al[j][2]);
+            split_h2(wb.y, wb.x, Ah[j][3], Al[j][3]);
+            w = cmul64(w, z8);
+        }
+    }
+    double buf = s.databuf[ev];  // replicated over the 4 lanes of vehicle g
+    const float coef = (float)(s.amp[ev] / (kSigma * kSigma));  // SARL:157-159
+    const long long step0 = s.step_ctr[e];
+    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
+    const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);  // SARL:331
+    const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));        // SARL:318-319
+    const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
+    const double tf = p.time_fast;
+    const unsigned sV = (unsigned)E * V;
+    const unsigned o_lane = (unsigned)e * V + g + 2u * tig * sV;  // + t0 * sV: trace offset of my first step
+    const unsigned r_lane = (unsigned)e + 2u * tig * E;
+
+    // one 8-step tile: rows [rb, rb + 8) of the stage at `st`, steps tb .. tb + 7 of the rollout
+    auto epilogue = [&](const float (&accM)[4], const float (&accX)[4], const unsigned char* st, int rb, int tb) {
+        const float* ac = reinterpret_cast<const float*>(st + PH_BYTES) + (rb + 2 * tig) * (2 * V) + g;
+        const int* ar = reinterpret_cast<const int*>(st + PH_BYTES + AC_BYTES) + (rb + 2 * tig) * V + g;
+        const float2 a0 = make_float2(ac[0], ac[2 * V]), a1 = make_float2(ac[V], ac[3 * V]);
+        const int arr0 = ar[0], arr1 = ar[V];
+        const bool ok0 = tb + 2 * tig < T, ok1 = tb + 2 * tig + 1 < T;
+        // S_g of steps tb + 2 tig (acc[0] + j acc[2]) and tb + 2 tig + 1 (acc[1] + j acc[3]), both steps packed
+        const float2 re = __fadd2_rn(make_float2(accM[0], accM[1]), make_float2(accX[0], accX[1]));
+        const float2 im = __fadd2_rn(make_float2(accM[2], accM[3]), make_float2(accX[2], accX[3]));
+        const float2 g2 = __ffma2_rn(re, re, __fmul2_rn(im, im));
+        const float2 y = __fadd2_rn(f2(1.0f), __fmul2_rn(a0, __fmul2_rn(f2(coef), g2)));  // SARL:159
+        const float2 rate = __fmul2_rn(make_float2(__log2f(y.x), __log2f(y.y)), f2(0.693147180559945309f));
+        const float2 dt = __fmul2_rn(rate, f2(c_dt));
+        const float2 dp = __fmul2_rn(make_float2(cbrt_sfu(a1.x), cbrt_sfu(a1.y)), f2(c_dp));  // SARL:331
+        // steps past the end of the rollout are identity steps (DataBuf >= 0)
+        const double d0 = ok0 ? __dadd_rn((double)dt.x, (double)dp.x) : 0.0;
+        const double d1 = ok1 ? __dadd_rn((double)dt.y, (double)dp.y) : 0.0;
+        const double i0 = ok0 ? __dmul_rn(__dmul_rn((double)arr0, tf), 1000.0) : 0.0;
+        const double i1 = ok1 ? __dmul_rn(__dmul_rn((double)arr1, tf), 1000.0) : 0.0;
+        // ---- DataBuf at my first step: inclusive scan of the lanes' two-step maps over tig = 0..3
+        MaxPlus f = mp_then(MaxPlus{i0 - d0, i0}, MaxPlus{i1 - d1, i1});
+        {
+            MaxPlus q{__shfl_up_sync(kFull, f.a, 1, 4), __shfl_up_sync(kFull, f.b, 1, 4)};
+            if (tig >= 1) f = mp_then(q, f);
+            q = MaxPlus{__shfl_up_sync(kFull, f.a, 2, 4), __shfl_up_sync(kFull, f.b, 2, 4)};
+            if (tig >= 2) f = mp_then(q, f);
+        }
+        const MaxPlus ex{__shfl_up_sync(kFull, f.a, 1, 4), __shfl_up_sync(kFull, f.b, 1, 4)};  // maps before mine
+        const MaxPlus all{__shfl_sync(kFull, f.a, 3, 4), __shfl_sync(kFull, f.b, 3, 4)};       // the whole tile
+        double cur = tig == 0 ? buf : mp_apply(ex, buf);
+        buf = mp_apply(all, buf);
+        // ---- my two steps in the reference's order (SARL:333-358)
+        float rew[2];
+        const unsigned o = o_lane + (unsigned)tb * sV;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double dd = i ? d1 : d0, inc = i ? i1 : i0;
+            const float a0i = i ? a0.y : a0.x, a1i = i ? a1.y : a1.x, dpi = i ? dp.y : dp.x;
+            const double raw = __dsub_rn(cur, dd);  // SARL:334
+            const bool neg = raw < 0.0;
+            const float b = __fmul_rn((float)fmax(0.0, raw + (double)dpi), c_rev);
+            const float overp = neg ? __fsub_rn(a1i, __fmul_rn(__fmul_rn(b, b), b)) : 0.f;  // SARL:336-339
+            const float overd = neg ? (float)(-raw) : 0.f;
+            const double nb = neg ? 0.0 : raw;
+            const float base = __fsub_rn(-__fmul_rn(t1, __fadd_rn(a0i, a1i)), __fmul_rn(t2, (float)nb));
+            const float pen = (nb > 0.0) ? pen1 : ((overd > 2.0f) ? pen2 : 0.f);  // SARL:343-352
+            rew[i] = __fsub_rn(base, pen);
+            cur = __dadd_rn(nb, inc);  // SARL:354-356
+            if (i ? ok1 : ok0) {
+                const unsigned oi = o + (i ? sV : 0u);
+                a.out.DataBuf[oi] = (float)cur;
+                a.out.data_t[oi] = i ? dt.y : dt.x;
+                a.out.data_p[oi] = dpi;
+                a.out.over_power[oi] = overp;
+                a.out.over_data[oi] = overd;
+                a.out.rate[oi] = i ? rate.y : rate.x;
+                if (tb + 2 * tig + i == T - 1) {  // the reference object's attributes after the last step
+                    s.rate[ev] = i ? rate.y : rate.x;
+                    s.data_t[ev] = i ? dt.y : dt.x;
+                    s.data_p[ev] = dpi;
+                    s.over_power[ev] = overp;
+                    s.over_data[ev] = overd;
+                    s.data_r[ev] = i ? arr1 : arr0;
+                }
+            }
+        }
+        // mean over the vehicles (lanes g = 0..7 of the same tig): same tree as seg_sum<8>
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            rew[i] += __shfl_xor_sync(kFull, rew[i], 4);
+            rew[i] += __shfl_xor_sync(kFull, rew[i], 8);
+            rew[i] += __shfl_xor_sync(kFull, rew[i], 16);
+            rew[i] = __fmul_rn(rew[i], 0.125f);
+        }
+        if (g == 0) {
+            const unsigned ro = r_lane + (unsigned)tb * E;
+            if (ok0) a.out.reward[ro] = rew[0];
+            if (ok1) a.out.reward[ro + E] = rew[1];
+            if (tb + 2 * tig == T - 1) s.reward[e] = rew[0];
+            if (tb + 2 * tig + 1 == T - 1) s.reward[e] = rew[1];
+        }
+    };
+
+    for (int k = 0; k < NS; ++k) {
+        if (lane == 0 && k + STAGES - 1 < NS) {  // refill the stage the previous iteration consumed
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(k + STAGES - 1);
+        }
+        mbar_wait(bars + 8 * (k % STAGES), (uint32_t)(k / STAGES) & 1u);
+        const unsigned char* st = ring_g + (k % STAGES) * STAGE_BYTES;
+        const float* ph = reinterpret_cast<const float*>(st) + g * M + 2 * tig;  // B column g = step 16 k + g
+        float mA[4] = {0.f, 0.f, 0.f, 0.f}, xA[4] = {0.f, 0.f, 0.f, 0.f};
+        float mB[4] = {0.f, 0.f, 0.f, 0.f}, xB[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            const float2 pa = *reinterpret_cast<const float2*>(ph + 8 * j);
+            const float2 pb = *reinterpret_cast<const float2*>(ph + 8 * M + 8 * j);
+            float2 sn, cs;
+            uint32_t b0h, b0l, b1h, b1l;
+            sincos_pi2(pa, &sn, &cs);  // theta = exp(j*phase) of elements 8 j + 2 tig + {0, 1} (SARL:125-131)
+            split_h2(cs.x, sn.x, b0h, b0l);
+            split_h2(cs.y, sn.y, b1h, b1l);
+            mma_16816(mA, Ah[j], b0h, b1h);
+            mma_16816(xA, Ah[j], b0l, b1l);
+            mma_16816(xA, Al[j], b0h, b1h);
+            sincos_pi2(pb, &sn, &cs);
+            split_h2(cs.x, sn.x, b0h, b0l);
+            split_h2(cs.y, sn.y, b1h, b1l);
+            mma_16816(mB, Ah[j], b0h, b1h);
+            mma_16816(xB, Ah[j], b0l, b1l);
+            mma_16816(xB, Al[j], b0h, b1h);
+        }
+        epilogue(mA, xA, st, 0, k * R);
+        epilogue(mB, xB, st, 8, k * R + 8);
+        __syncwarp();  // every lane is done with the stage before lane 0 re-arms it
+    }
+
+    // ---- registers -> state
+    for (int m = lane; m < M; m += 32)  // elements_phase_shift_real = the last action_phase (SARL:128)
+        s.phase_real[(size_t)e * M + m] = __ldg(a.phase + ((size_t)(T - 1) * E + e) * M + m);
+    if (tig == 0) s.databuf[ev] = buf;
+    if (lane == 0) s.step_ctr[e] = step0 + T;
 }
 
 }  // namespace risvec

@@ -35,7 +35,8 @@ def _sarl_env(path, E, V, M):
 
 
 # every SARL step kernel at BASELINE size: (path, M, kernel it must run)
-SARL_PATHS = [("mma", 40, "k_sarl_mma"), ("v8", 40, "k_sarl_v8"), ("packed", 40, "k_sarl_v8"),
+SARL_PATHS = [("mma", 40, "k_sarl_mma_tma"), ("mma-ldg", 40, "k_sarl_mma"), ("mma", 16, "k_sarl_mma_tma"),
+              ("mma", 24, "k_sarl_mma"), ("v8", 40, "k_sarl_v8"), ("packed", 40, "k_sarl_v8"),
               ("generic", 40, "k_sarl_rollout"), ("generic", 64, "k_sarl_cascade2+k_sarl_scan")]
 
 

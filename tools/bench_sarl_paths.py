@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--V", type=int, default=8)
     ap.add_argument("--M", type=int, default=40)
     ap.add_argument("--reps", type=int, default=50)
-    ap.add_argument("--paths", default="mma,v8,packed")
+    ap.add_argument("--paths", default="mma,mma-ldg,v8,packed")
     args = ap.parse_args()
     E, V, M, T = args.envs, args.V, args.M, args.T
     dev = torch.device("cuda", 0)

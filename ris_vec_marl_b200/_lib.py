@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("RISVEC_LIB") or os.path.join(PKG_DIR, "librisvec.so")
 SOURCES = ["risvec.cu"]
 HEADERS = ["common.cuh", "geom.cuh", "ris.cuh", "step.cuh", "sarl_mma.cuh", "pairing.cuh", "replay.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared"]
+              "-shared", "-split-compile", "0"]
 
 MAX_LANES = 8
 NSTAT = 16

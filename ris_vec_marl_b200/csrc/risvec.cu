@@ -259,13 +259,13 @@ int launch_sarl_mma_tma(risvec_env* env, const SarlArgs& a, cudaStream_t st, boo
         !tensor_map_2d(&tm_ar, CU_TENSOR_MAP_DATA_TYPE_INT32, a.arrivals, (uint64_t)E * V, T, V, kSarlTmaRows))
         return RISVEC_OK;  // not encodable here: the caller falls back to the LDG kernel
     auto kern = k_sarl_mma_tma<KT, kSarlTmaStages>;
-    const int smem = 4 * kSarlTmaStages * sarl_tma_stage_bytes(KT) + 4 * kSarlTmaStages * 8 + 128;
+    const int smem = kSarlTmaStages * sarl_tma_stage_bytes(KT) + kSarlTmaStages * 8 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    kern<<<(E + 3) / 4, 128, smem, st>>>(env->dims, env->st, env->params, a, tm_ph, tm_ac, tm_ar);
+    kern<<<E, 32, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm_ph, tm_ac, tm_ar);
     *launched = true;
     return check_step_launch(env, "k_sarl_mma_tma");
 }

@@ -348,28 +348,53 @@ __device__ __forceinline__ double mp_apply(const MaxPlus& f, double x) {
     return y > f.b ? y : f.b;
 }
 
+// scalar constants of the step, formed on the host in float64 and rounded once: as kernel parameters they
+// sit in the constant bank and are used as instruction operands (no registers, no in-kernel conversions)
+struct SarlConsts {
+    float c_dt;    // time_fast * bandwidth * 1000        (SARL:160, data_t = rate * c_dt)
+    float c_dp;    // cbrt(1 / k) * time_fast / L / 1000  (SARL:331)
+    float c_rev;   // 1000 * L / time_fast * cbrt(k)      (SARL:318-319)
+    float nt1, nt2;  // -t_factor1, -t_factor2            (SARL:341-352)
+    float pen1, pen2;
+    float _pad;
+    double tf;     // time_fast
+};
+inline SarlConsts sarl_consts(const risvec_params_t& p) {
+    SarlConsts c;
+    c.c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
+    c.c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);
+    c.c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));
+    c.nt1 = -(float)p.t_factor1;
+    c.nt2 = -(float)p.t_factor2;
+    c.pen1 = (float)p.penalty1;
+    c.pen2 = (float)p.penalty2;
+    c._pad = 0.f;
+    c.tf = p.time_fast;
+    return c;
+}
+
 constexpr int kSarlTmaRows = 16;  // steps per stage (two 8-step mma tiles)
 __host__ __device__ constexpr int sarl_tma_stage_bytes(int KT) { return kSarlTmaRows * (8 * KT + 16 + 8) * 4; }
 
 template <int KT, int STAGES>
-__global__ void __launch_bounds__(128, 4)
-    k_sarl_mma_tma(Dims d, State s, risvec_params_t p, SarlArgs a, const __grid_constant__ CUtensorMap tm_ph,
+__global__ void __launch_bounds__(32, 16)
+    k_sarl_mma_tma(Dims d, State s, const SarlConsts c, SarlArgs a, const __grid_constant__ CUtensorMap tm_ph,
                    const __grid_constant__ CUtensorMap tm_ac, const __grid_constant__ CUtensorMap tm_ar) {
     constexpr int M = 8 * KT, V = 8, R = kSarlTmaRows;
     constexpr int PH_BYTES = R * M * 4, AC_BYTES = R * 2 * V * 4, AR_BYTES = R * V * 4;
     constexpr int STAGE_BYTES = PH_BYTES + AC_BYTES + AR_BYTES;
     static_assert(STAGE_BYTES == sarl_tma_stage_bytes(KT) && STAGE_BYTES % 128 == 0, "");
     extern __shared__ unsigned char sarl_tma_smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    // block = ONE warp = one env (4096 small blocks balance the tail of the grid over the 148 SMs far
+    // better than 1024 blocks of four warps: the warps of a block do not interact anyway)
+    const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
     const int E = d.E, T = a.T;
-    const int e = blockIdx.x * 4 + warp;
-    if (e >= E) return;  // warps are independent: no block-level synchronisation below
+    const int e = blockIdx.x;
 
-    // ---- this warp's stage ring + its mbarriers (128 B aligned for the TMA destinations)
-    const uint32_t smem0 = (smem_u32(sarl_tma_smem_raw) + 127u) & ~127u;
-    const uint32_t ring = smem0 + (uint32_t)warp * (STAGES * STAGE_BYTES);
-    const uint32_t bars = smem0 + 4u * (STAGES * STAGE_BYTES) + (uint32_t)warp * (STAGES * 8);
-    const unsigned char* ring_g = sarl_tma_smem_raw + (smem0 - smem_u32(sarl_tma_smem_raw)) + warp * (STAGES * STAGE_BYTES);
+    // ---- the stage ring + its mbarriers (128 B aligned for the TMA destinations)
+    const uint32_t ring = (smem_u32(sarl_tma_smem_raw) + 127u) & ~127u;
+    const uint32_t bars = ring + STAGES * STAGE_BYTES;
+    const unsigned char* ring_g = sarl_tma_smem_raw + (ring - smem_u32(sarl_tma_smem_raw));
     if (lane == 0) {
 #pragma unroll
         for (int st = 0; st < STAGES; ++st) mbar_init(bars + 8 * st, 1);
@@ -410,114 +435,31 @@ __global__ void __launch_bounds__(128, 4)
     }
     double buf = s.databuf[ev];  // replicated over the 4 lanes of vehicle g
     const float coef = (float)(s.amp[ev] / (kSigma * kSigma));  // SARL:157-159
-    const long long step0 = s.step_ctr[e];
-    const float c_dt = (float)(p.time_fast * p.bandwidth * 1000.0);
-    const float c_dp = (float)(cbrt(1.0 / p.k) * p.time_fast / p.L / 1000.0);  // SARL:331
-    const float c_rev = (float)(1000.0 * p.L / p.time_fast * cbrt(p.k));        // SARL:318-319
-    const float t1 = (float)p.t_factor1, t2 = (float)p.t_factor2, pen1 = (float)p.penalty1, pen2 = (float)p.penalty2;
-    const double tf = p.time_fast;
     const unsigned sV = (unsigned)E * V;
-    const unsigned o_lane = (unsigned)e * V + g + 2u * tig * sV;  // + t0 * sV: trace offset of my first step
-    const unsigned r_lane = (unsigned)e + 2u * tig * E;
+    const unsigned o_lane = (unsigned)e * V + g + 4u * tig * sV;  // + t0 * sV: trace offset of my first step
+    const unsigned r_lane = (unsigned)e + 4u * tig * E;
 
-    // one 8-step tile: rows [rb, rb + 8) of the stage at `st`, steps tb .. tb + 7 of the rollout
-    auto epilogue = [&](const float (&accM)[4], const float (&accX)[4], const unsigned char* st, int rb, int tb) {
-        const float* ac = reinterpret_cast<const float*>(st + PH_BYTES) + (rb + 2 * tig) * (2 * V) + g;
-        const int* ar = reinterpret_cast<const int*>(st + PH_BYTES + AC_BYTES) + (rb + 2 * tig) * V + g;
-        const float2 a0 = make_float2(ac[0], ac[2 * V]), a1 = make_float2(ac[V], ac[3 * V]);
-        const int arr0 = ar[0], arr1 = ar[V];
-        const bool ok0 = tb + 2 * tig < T, ok1 = tb + 2 * tig + 1 < T;
-        // S_g of steps tb + 2 tig (acc[0] + j acc[2]) and tb + 2 tig + 1 (acc[1] + j acc[3]), both steps packed
-        const float2 re = __fadd2_rn(make_float2(accM[0], accM[1]), make_float2(accX[0], accX[1]));
-        const float2 im = __fadd2_rn(make_float2(accM[2], accM[3]), make_float2(accX[2], accX[3]));
-        const float2 g2 = __ffma2_rn(re, re, __fmul2_rn(im, im));
-        const float2 y = __fadd2_rn(f2(1.0f), __fmul2_rn(a0, __fmul2_rn(f2(coef), g2)));  // SARL:159
-        const float2 rate = __fmul2_rn(make_float2(__log2f(y.x), __log2f(y.y)), f2(0.693147180559945309f));
-        const float2 dt = __fmul2_rn(rate, f2(c_dt));
-        const float2 dp = __fmul2_rn(make_float2(cbrt_sfu(a1.x), cbrt_sfu(a1.y)), f2(c_dp));  // SARL:331
-        // steps past the end of the rollout are identity steps (DataBuf >= 0)
-        const double d0 = ok0 ? __dadd_rn((double)dt.x, (double)dp.x) : 0.0;
-        const double d1 = ok1 ? __dadd_rn((double)dt.y, (double)dp.y) : 0.0;
-        const double i0 = ok0 ? __dmul_rn(__dmul_rn((double)arr0, tf), 1000.0) : 0.0;
-        const double i1 = ok1 ? __dmul_rn(__dmul_rn((double)arr1, tf), 1000.0) : 0.0;
-        // ---- DataBuf at my first step: inclusive scan of the lanes' two-step maps over tig = 0..3
-        MaxPlus f = mp_then(MaxPlus{i0 - d0, i0}, MaxPlus{i1 - d1, i1});
-        {
-            MaxPlus q{__shfl_up_sync(kFull, f.a, 1, 4), __shfl_up_sync(kFull, f.b, 1, 4)};
-            if (tig >= 1) f = mp_then(q, f);
-            q = MaxPlus{__shfl_up_sync(kFull, f.a, 2, 4), __shfl_up_sync(kFull, f.b, 2, 4)};
-            if (tig >= 2) f = mp_then(q, f);
-        }
-        const MaxPlus ex{__shfl_up_sync(kFull, f.a, 1, 4), __shfl_up_sync(kFull, f.b, 1, 4)};  // maps before mine
-        const MaxPlus all{__shfl_sync(kFull, f.a, 3, 4), __shfl_sync(kFull, f.b, 3, 4)};       // the whole tile
-        double cur = tig == 0 ? buf : mp_apply(ex, buf);
-        buf = mp_apply(all, buf);
-        // ---- my two steps in the reference's order (SARL:333-358)
-        float rew[2];
-        const unsigned o = o_lane + (unsigned)tb * sV;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const double dd = i ? d1 : d0, inc = i ? i1 : i0;
-            const float a0i = i ? a0.y : a0.x, a1i = i ? a1.y : a1.x, dpi = i ? dp.y : dp.x;
-            const double raw = __dsub_rn(cur, dd);  // SARL:334
-            const bool neg = raw < 0.0;
-            const float b = __fmul_rn((float)fmax(0.0, raw + (double)dpi), c_rev);
-            const float overp = neg ? __fsub_rn(a1i, __fmul_rn(__fmul_rn(b, b), b)) : 0.f;  // SARL:336-339
-            const float overd = neg ? (float)(-raw) : 0.f;
-            const double nb = neg ? 0.0 : raw;
-            const float base = __fsub_rn(-__fmul_rn(t1, __fadd_rn(a0i, a1i)), __fmul_rn(t2, (float)nb));
-            const float pen = (nb > 0.0) ? pen1 : ((overd > 2.0f) ? pen2 : 0.f);  // SARL:343-352
-            rew[i] = __fsub_rn(base, pen);
-            cur = __dadd_rn(nb, inc);  // SARL:354-356
-            if (i ? ok1 : ok0) {
-                const unsigned oi = o + (i ? sV : 0u);
-                a.out.DataBuf[oi] = (float)cur;
-                a.out.data_t[oi] = i ? dt.y : dt.x;
-                a.out.data_p[oi] = dpi;
-                a.out.over_power[oi] = overp;
-                a.out.over_data[oi] = overd;
-                a.out.rate[oi] = i ? rate.y : rate.x;
-                if (tb + 2 * tig + i == T - 1) {  // the reference object's attributes after the last step
-                    s.rate[ev] = i ? rate.y : rate.x;
-                    s.data_t[ev] = i ? dt.y : dt.x;
-                    s.data_p[ev] = dpi;
-                    s.over_power[ev] = overp;
-                    s.over_data[ev] = overd;
-                    s.data_r[ev] = i ? arr1 : arr0;
-                }
-            }
-        }
-        // mean over the vehicles (lanes g = 0..7 of the same tig): same tree as seg_sum<8>
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            rew[i] += __shfl_xor_sync(kFull, rew[i], 4);
-            rew[i] += __shfl_xor_sync(kFull, rew[i], 8);
-            rew[i] += __shfl_xor_sync(kFull, rew[i], 16);
-            rew[i] = __fmul_rn(rew[i], 0.125f);
-        }
-        if (g == 0) {
-            const unsigned ro = r_lane + (unsigned)tb * E;
-            if (ok0) a.out.reward[ro] = rew[0];
-            if (ok1) a.out.reward[ro + E] = rew[1];
-            if (tb + 2 * tig == T - 1) s.reward[e] = rew[0];
-            if (tb + 2 * tig + 1 == T - 1) s.reward[e] = rew[1];
-        }
-    };
-
-    for (int k = 0; k < NS; ++k) {
+    // The 16 steps of a stage are spread over the two mma tiles so that lane (g, tig) ends up with FOUR
+    // CONSECUTIVE steps 4 tig .. 4 tig + 3 of vehicle g: column c of tile A is step 4 (c >> 1) + (c & 1),
+    // column c of tile B the step two later (the accumulator columns of a lane are 2 tig and 2 tig + 1).
+    // TAIL = the stage may reach past step T - 1 (identity steps, guarded stores) and holds the last
+    // step, whose values become the env's state; all other stages run without a single branch.
+    auto stage = [&](auto tail_tag, int k) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
         if (lane == 0 && k + STAGES - 1 < NS) {  // refill the stage the previous iteration consumed
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(k + STAGES - 1);
         }
         mbar_wait(bars + 8 * (k % STAGES), (uint32_t)(k / STAGES) & 1u);
         const unsigned char* st = ring_g + (k % STAGES) * STAGE_BYTES;
-        const float* ph = reinterpret_cast<const float*>(st) + g * M + 2 * tig;  // B column g = step 16 k + g
+        // ---- cascaded reduction: B column g of tile A = row 4 (g >> 1) + (g & 1), of tile B two rows later
+        const float* ph = reinterpret_cast<const float*>(st) + (4 * (g >> 1) + (g & 1)) * M + 2 * tig;
         float mA[4] = {0.f, 0.f, 0.f, 0.f}, xA[4] = {0.f, 0.f, 0.f, 0.f};
         float mB[4] = {0.f, 0.f, 0.f, 0.f}, xB[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < KT; ++j) {
             const float2 pa = *reinterpret_cast<const float2*>(ph + 8 * j);
-            const float2 pb = *reinterpret_cast<const float2*>(ph + 8 * M + 8 * j);
+            const float2 pb = *reinterpret_cast<const float2*>(ph + 2 * M + 8 * j);
             float2 sn, cs;
             uint32_t b0h, b0l, b1h, b1l;
             sincos_pi2(pa, &sn, &cs);  // theta = exp(j*phase) of elements 8 j + 2 tig + {0, 1} (SARL:125-131)
@@ -533,16 +475,127 @@ __global__ void __launch_bounds__(128, 4)
             mma_16816(xB, Ah[j], b0l, b1l);
             mma_16816(xB, Al[j], b0h, b1h);
         }
-        epilogue(mA, xA, st, 0, k * R);
-        epilogue(mB, xB, st, 8, k * R + 8);
+        // ---- per-step part for my steps tb + {0,1,2,3}, as packed pairs (0,1) from tile A, (2,3) from tile B
+        const int tb = k * R + 4 * tig;
+        const float* ac = reinterpret_cast<const float*>(st + PH_BYTES) + (4 * tig) * (2 * V) + g;
+        const int* ar = reinterpret_cast<const int*>(st + PH_BYTES + AC_BYTES) + (4 * tig) * V + g;
+        float2 a0[2], a1[2], rate[2], dt[2], dp[2];
+        int arr[4];
+        double dd[4], inc[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float(&accM)[4] = h ? mB : mA;
+            const float(&accX)[4] = h ? xB : xA;
+            a0[h] = make_float2(ac[(2 * h) * 2 * V], ac[(2 * h + 1) * 2 * V]);
+            a1[h] = make_float2(ac[(2 * h) * 2 * V + V], ac[(2 * h + 1) * 2 * V + V]);
+            arr[2 * h] = ar[(2 * h) * V];
+            arr[2 * h + 1] = ar[(2 * h + 1) * V];
+            const float2 re = __fadd2_rn(make_float2(accM[0], accM[1]), make_float2(accX[0], accX[1]));
+            const float2 im = __fadd2_rn(make_float2(accM[2], accM[3]), make_float2(accX[2], accX[3]));
+            const float2 g2 = __ffma2_rn(re, re, __fmul2_rn(im, im));
+            const float2 y = __fadd2_rn(f2(1.0f), __fmul2_rn(a0[h], __fmul2_rn(f2(coef), g2)));  // SARL:159
+            rate[h] = __fmul2_rn(make_float2(__log2f(y.x), __log2f(y.y)), f2(0.693147180559945309f));
+            dt[h] = __fmul2_rn(rate[h], f2(c.c_dt));
+            dp[h] = __fmul2_rn(make_float2(cbrt_sfu(a1[h].x), cbrt_sfu(a1[h].y)), f2(c.c_dp));  // SARL:331
+        }
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ok[i] = !TAIL || tb + i < T;  // steps past the end of the rollout are identity steps (DataBuf >= 0)
+            const float dti = (i & 1) ? dt[i >> 1].y : dt[i >> 1].x, dpi = (i & 1) ? dp[i >> 1].y : dp[i >> 1].x;
+            dd[i] = ok[i] ? __dadd_rn((double)dti, (double)dpi) : 0.0;
+            inc[i] = ok[i] ? __dmul_rn(__dmul_rn((double)arr[i], c.tf), 1000.0) : 0.0;
+        }
+        // ---- DataBuf at my first step: inclusive scan of the lanes' four-step maps over tig = 0..3
+        MaxPlus f = mp_then(mp_then(MaxPlus{inc[0] - dd[0], inc[0]}, MaxPlus{inc[1] - dd[1], inc[1]}),
+                            mp_then(MaxPlus{inc[2] - dd[2], inc[2]}, MaxPlus{inc[3] - dd[3], inc[3]}));
+        {
+            MaxPlus q{__shfl_up_sync(kFull, f.a, 1, 4), __shfl_up_sync(kFull, f.b, 1, 4)};
+            const MaxPlus f1 = mp_then(q, f);
+            if (tig >= 1) f = f1;
+            q = MaxPlus{__shfl_up_sync(kFull, f.a, 2, 4), __shfl_up_sync(kFull, f.b, 2, 4)};
+            const MaxPlus f2m = mp_then(q, f);
+            if (tig >= 2) f = f2m;
+        }
+        const MaxPlus ex{__shfl_up_sync(kFull, f.a, 1, 4), __shfl_up_sync(kFull, f.b, 1, 4)};  // maps before mine
+        const MaxPlus all{__shfl_sync(kFull, f.a, 3, 4), __shfl_sync(kFull, f.b, 3, 4)};       // the whole stage
+        const double xin = mp_apply(ex, buf);
+        double cur = tig == 0 ? buf : xin;
+        buf = mp_apply(all, buf);
+        // ---- my four steps in the reference's order (SARL:333-358)
+        float overd[4], nbf[4], barg[4], curf[4];
+        bool pos[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float dpi = (i & 1) ? dp[i >> 1].y : dp[i >> 1].x;
+            const double raw = __dsub_rn(cur, dd[i]);  // SARL:334
+            const bool neg = raw < 0.0;
+            pos[i] = raw > 0.0;
+            barg[i] = fmaxf(0.f, (float)(raw + (double)dpi));  // argument of localProcRev (SARL:337)
+            const float rawf = (float)raw;
+            overd[i] = fmaxf(0.f, -rawf);                      // over_data = -DataBuf where it went negative
+            nbf[i] = fmaxf(0.f, rawf);
+            cur = __dadd_rn(neg ? 0.0 : raw, inc[i]);          // SARL:354-356
+            curf[i] = (float)cur;
+        }
+        float rew[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 b = __fmul2_rn(make_float2(barg[2 * h], barg[2 * h + 1]), f2(c.c_rev));
+            const float2 b3 = __fmul2_rn(__fmul2_rn(b, b), b);
+            const float2 op = __fadd2_rn(a1[h], make_float2(-b3.x, -b3.y));  // SARL:336-339
+            const float2 base = __ffma2_rn(make_float2(nbf[2 * h], nbf[2 * h + 1]), f2(c.nt2),
+                                           __fmul2_rn(__fadd2_rn(a0[h], a1[h]), f2(c.nt1)));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = 2 * h + u;
+                const float od = overd[i];
+                const float overp = od > 0.f ? (u ? op.y : op.x) : 0.f;  // only where the buffer went negative
+                const float pen = pos[i] ? c.pen1 : ((od > 2.0f) ? c.pen2 : 0.f);  // SARL:343-352
+                rew[i] = __fsub_rn(u ? base.y : base.x, pen);
+                if (ok[i]) {
+                    const unsigned oi = o_lane + (unsigned)(k * R + i) * sV;
+                    a.out.DataBuf[oi] = curf[i];
+                    a.out.data_t[oi] = u ? dt[h].y : dt[h].x;
+                    a.out.data_p[oi] = u ? dp[h].y : dp[h].x;
+                    a.out.over_power[oi] = overp;
+                    a.out.over_data[oi] = od;
+                    a.out.rate[oi] = u ? rate[h].y : rate[h].x;
+                    if (TAIL && tb + i == T - 1) {  // the reference object's attributes after the last step
+                        s.rate[ev] = u ? rate[h].y : rate[h].x;
+                        s.data_t[ev] = u ? dt[h].y : dt[h].x;
+                        s.data_p[ev] = u ? dp[h].y : dp[h].x;
+                        s.over_power[ev] = overp;
+                        s.over_data[ev] = od;
+                        s.data_r[ev] = arr[i];
+                    }
+                }
+            }
+        }
+        // mean over the vehicles (lanes g = 0..7 of the same tig): same tree as seg_sum<8>
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            rew[i] += __shfl_xor_sync(kFull, rew[i], 4);
+            rew[i] += __shfl_xor_sync(kFull, rew[i], 8);
+            rew[i] += __shfl_xor_sync(kFull, rew[i], 16);
+            rew[i] = __fmul_rn(rew[i], 0.125f);
+        }
+        {  // every lane of a tig group holds the four means: lane g < 4 stores the one of step tb + g
+            const float r01 = (g & 1) ? rew[1] : rew[0], r23 = (g & 1) ? rew[3] : rew[2];
+            const float mine = (g & 2) ? r23 : r01;
+            if (g < 4 && (!TAIL || tb + g < T)) a.out.reward[r_lane + (unsigned)(k * R + g) * E] = mine;
+            if (TAIL && g < 4 && tb + g == T - 1) s.reward[e] = mine;
+        }
         __syncwarp();  // every lane is done with the stage before lane 0 re-arms it
-    }
+    };
+    for (int k = 0; k < NS - 1; ++k) stage(std::false_type{}, k);
+    stage(std::true_type{}, NS - 1);
 
     // ---- registers -> state
     for (int m = lane; m < M; m += 32)  // elements_phase_shift_real = the last action_phase (SARL:128)
         s.phase_real[(size_t)e * M + m] = __ldg(a.phase + ((size_t)(T - 1) * E + e) * M + m);
     if (tig == 0) s.databuf[ev] = buf;
-    if (lane == 0) s.step_ctr[e] = step0 + T;
+    if (lane == 0) s.step_ctr[e] += T;
 }
 
 }  // namespace risvec

@@ -248,35 +248,42 @@ bool tensor_map_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uin
            CUDA_SUCCESS;
 }
 
-constexpr int kSarlTmaStages = 3;
 template <int KT>
 int launch_sarl_mma_tma(risvec_env* env, const SarlArgs& a, cudaStream_t st, bool* launched) {
     *launched = false;
     const int E = env->dims.E, V = env->dims.V, M = env->dims.M, T = a.T;
     CUtensorMap tm_ph, tm_ac, tm_ar;
-    if (!tensor_map_2d(&tm_ph, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.phase, (uint64_t)E * M, T, M, kSarlTmaRows) ||
-        !tensor_map_2d(&tm_ac, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.action, (uint64_t)E * 2 * V, T, 2 * V, kSarlTmaRows) ||
-        !tensor_map_2d(&tm_ar, CU_TENSOR_MAP_DATA_TYPE_INT32, a.arrivals, (uint64_t)E * V, T, V, kSarlTmaRows))
-        return RISVEC_OK;  // not encodable here: the caller falls back to the LDG kernel
-    auto kern = k_sarl_mma_tma<KT, kSarlTmaStages>;
-    const int smem = kSarlTmaStages * sarl_tma_stage_bytes(KT) + kSarlTmaStages * 8 + 128;
+    SarlOutMaps tm_out;
+    const risvec_sarl_out_t& o = a.out;
+    float* const traces[6] = {o.DataBuf, o.data_t, o.data_p, o.over_power, o.over_data, o.rate};
+    bool ok = tensor_map_2d(&tm_ph, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.phase, (uint64_t)E * M, T, M, kSarlTmaRows) &&
+              tensor_map_2d(&tm_ac, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.action, (uint64_t)E * 2 * V, T, 2 * V, kSarlTmaRows) &&
+              tensor_map_2d(&tm_ar, CU_TENSOR_MAP_DATA_TYPE_INT32, a.arrivals, (uint64_t)E * V, T, V, kSarlTmaRows) &&
+              tensor_map_2d(&tm_out.reward, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, o.reward, (uint64_t)E, T, 4, kSarlTmaRows);
+    for (int n = 0; n < 6 && ok; ++n)  // the block's four envs x 8 vehicles = one 128-byte line per (trace, step)
+        ok = tensor_map_2d(&tm_out.trace[n], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, traces[n], (uint64_t)E * V, T, 4 * V, kSarlTmaRows);
+    if (!ok) return RISVEC_OK;  // not encodable here: the caller falls back to the LDG kernel
+    auto kern = k_sarl_mma_tma<KT>;
+    const int smem = sarl_tma_smem_bytes(KT);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    kern<<<E, 32, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm_ph, tm_ac, tm_ar);
+    kern<<<E / 4, 128, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm_ph, tm_ac, tm_ar, tm_out);
     *launched = true;
     return check_step_launch(env, "k_sarl_mma_tma");
 }
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
-// the TMA kernel covers the BASELINE shape: V = 8, M = 16 or 40, every trace + the arrivals supplied,
-// 16-byte aligned streams, 32-bit element indices
+// the TMA kernel covers the BASELINE shape: V = 8, E % 4 == 0, M = 16 or 40, every trace + the arrivals
+// supplied, 16-byte aligned streams, 32-bit element indices
 inline bool sarl_tma_covers(const risvec_env* env, const SarlArgs& a) {
     const risvec_sarl_out_t& o = a.out;
     const int M = env->dims.M;
-    return env->dims.V == 8 && (M == 16 || M == 40) && a.arrivals && o.reward && o.DataBuf && o.data_t && o.data_p &&
-           o.over_power && o.over_data && o.rate && aligned16(a.phase) && aligned16(a.action) && aligned16(a.arrivals) &&
+    return env->dims.V == 8 && env->dims.E % 4 == 0 && (M == 16 || M == 40) && a.arrivals && o.reward && o.DataBuf &&
+           o.data_t && o.data_p && o.over_power && o.over_data && o.rate && aligned16(a.phase) && aligned16(a.action) &&
+           aligned16(a.arrivals) && aligned16(o.reward) && aligned16(o.DataBuf) && aligned16(o.data_t) &&
+           aligned16(o.data_p) && aligned16(o.over_power) && aligned16(o.over_data) && aligned16(o.rate) &&
            (uint64_t)a.T * env->dims.E * (M > 16 ? M : 16) < (1ull << 31);
 }
 inline bool sarl_mma_covers(const risvec_env* env) {

@@ -332,6 +332,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
                  ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
 // max-plus affine map x -> max(x + a, b): the DataBuf step x -> max(x - d, 0) + inc is (inc - d, inc)
 struct MaxPlus {
     double a, b;
@@ -373,28 +378,48 @@ inline SarlConsts sarl_consts(const risvec_params_t& p) {
     return c;
 }
 
-constexpr int kSarlTmaRows = 16;  // steps per stage (two 8-step mma tiles)
+constexpr int kSarlTmaRows = 16;    // steps per stage (two 8-step mma tiles)
+constexpr int kSarlTmaStages = 2;   // input stages per warp (one in use, one in flight)
 __host__ __device__ constexpr int sarl_tma_stage_bytes(int KT) { return kSarlTmaRows * (8 * KT + 16 + 8) * 4; }
+constexpr int kSarlOutTileBytes = 6 * kSarlTmaRows * 32 * 4 + kSarlTmaRows * 4 * 4;  // six traces [16][4 envs][8] + reward [16][4]
+__host__ __device__ constexpr int sarl_tma_smem_bytes(int KT) {
+    return 4 * kSarlTmaStages * sarl_tma_stage_bytes(KT) + kSarlOutTileBytes + 4 * kSarlTmaStages * 8 + 128;
+}
 
-template <int KT, int STAGES>
-__global__ void __launch_bounds__(32, 16)
+// output tensor maps of one rollout (order of the out tile in shared memory)
+struct SarlOutMaps {
+    CUtensorMap trace[6];  // DataBuf, data_t, data_p, over_power, over_data, rate: [T, E*8] f32, box {32, 16}
+    CUtensorMap reward;    // [T, E] f32, box {4, 16}
+};
+
+#ifndef RISVEC_TMA_MINB
+#define RISVEC_TMA_MINB 4  // resident blocks (of four warps) per SM the register allocation aims at
+#endif
+template <int KT>
+__global__ void __launch_bounds__(128, RISVEC_TMA_MINB)
     k_sarl_mma_tma(Dims d, State s, const SarlConsts c, SarlArgs a, const __grid_constant__ CUtensorMap tm_ph,
-                   const __grid_constant__ CUtensorMap tm_ac, const __grid_constant__ CUtensorMap tm_ar) {
-    constexpr int M = 8 * KT, V = 8, R = kSarlTmaRows;
+                   const __grid_constant__ CUtensorMap tm_ac, const __grid_constant__ CUtensorMap tm_ar,
+                   const __grid_constant__ SarlOutMaps tm_out) {
+    constexpr int M = 8 * KT, V = 8, R = kSarlTmaRows, STAGES = kSarlTmaStages;
     constexpr int PH_BYTES = R * M * 4, AC_BYTES = R * 2 * V * 4, AR_BYTES = R * V * 4;
     constexpr int STAGE_BYTES = PH_BYTES + AC_BYTES + AR_BYTES;
+    constexpr int TRACE_WORDS = R * 32;  // one trace of the out tile: [16 steps][4 envs][8 vehicles]
     static_assert(STAGE_BYTES == sarl_tma_stage_bytes(KT) && STAGE_BYTES % 128 == 0, "");
     extern __shared__ unsigned char sarl_tma_smem_raw[];
-    // block = ONE warp = one env (4096 small blocks balance the tail of the grid over the 148 SMs far
-    // better than 1024 blocks of four warps: the warps of a block do not interact anyway)
-    const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
+    // block = four warps = four ADJACENT envs (E % 4 == 0).  The warps only meet at the out tile.
+    const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
     const int E = d.E, T = a.T;
-    const int e = blockIdx.x;
+    const int e0 = blockIdx.x * 4, e = e0 + warp;
 
-    // ---- the stage ring + its mbarriers (128 B aligned for the TMA destinations)
-    const uint32_t ring = (smem_u32(sarl_tma_smem_raw) + 127u) & ~127u;
-    const uint32_t bars = ring + STAGES * STAGE_BYTES;
-    const unsigned char* ring_g = sarl_tma_smem_raw + (ring - smem_u32(sarl_tma_smem_raw));
+    // ---- shared memory: [4 warps][STAGES] input stages | out tile | mbarriers   (128 B aligned)
+    const uint32_t base = (smem_u32(sarl_tma_smem_raw) + 127u) & ~127u;
+    unsigned char* base_g = sarl_tma_smem_raw + (base - smem_u32(sarl_tma_smem_raw));
+    const uint32_t ring = base + (uint32_t)warp * (STAGES * STAGE_BYTES);
+    const unsigned char* ring_g = base_g + warp * (STAGES * STAGE_BYTES);
+    const uint32_t out_s = base + 4u * STAGES * STAGE_BYTES;
+    float* out_g = reinterpret_cast<float*>(base_g + 4 * STAGES * STAGE_BYTES);
+    const uint32_t bars = out_s + kSarlOutTileBytes + (uint32_t)warp * (STAGES * 8);
     if (lane == 0) {
 #pragma unroll
         for (int st = 0; st < STAGES; ++st) mbar_init(bars + 8 * st, 1);
@@ -403,7 +428,7 @@ __global__ void __launch_bounds__(32, 16)
     }
     __syncwarp();
     const int NS = (T + R - 1) / R;  // stages of 16 steps in this rollout
-    auto issue = [&](int k) {       // lane 0: the env's rows of steps [16 k, 16 k + 16) -> stage k % STAGES
+    auto issue = [&](int k) {       // lane 0: my env's rows of steps [16 k, 16 k + 16) -> stage k % STAGES
         const uint32_t dst = ring + (uint32_t)(k % STAGES) * STAGE_BYTES, bar = bars + 8 * (k % STAGES);
         mbar_expect_tx(bar, STAGE_BYTES);
         tma_load_2d(dst, &tm_ph, e * M, k * R, bar);
@@ -412,7 +437,7 @@ __global__ void __launch_bounds__(32, 16)
     };
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < STAGES - 1; ++k)
+        for (int k = 0; k < STAGES; ++k)
             if (k < NS) issue(k);
     }
 
@@ -435,21 +460,24 @@ __global__ void __launch_bounds__(32, 16)
     }
     double buf = s.databuf[ev];  // replicated over the 4 lanes of vehicle g
     const float coef = (float)(s.amp[ev] / (kSigma * kSigma));  // SARL:157-159
-    const unsigned sV = (unsigned)E * V;
-    const unsigned o_lane = (unsigned)e * V + g + 4u * tig * sV;  // + t0 * sV: trace offset of my first step
-    const unsigned r_lane = (unsigned)e + 4u * tig * E;
+    // my slots of the out tile: trace n at out_w[n * TRACE_WORDS + 32 i] for my step i = 0..3
+    float* const out_w = out_g + (4 * tig) * 32 + warp * 8 + g;
+    float* const out_r = out_g + 6 * TRACE_WORDS + (4 * tig) * 4 + warp;  // + 4 g': mean reward of step 4 tig + g'
 
-    // The 16 steps of a stage are spread over the two mma tiles so that lane (g, tig) ends up with FOUR
+    // values of the lane's latest step; those of step T - 1 become the env's state after the loop
+    struct LastStep {
+        float rate, dt, dp, overp, overd, rew;
+        int arr;
+        bool mine;  // this lane holds step T - 1
+    };
+    // One stage = 16 steps, spread over the two mma tiles so that lane (g, tig) ends up with FOUR
     // CONSECUTIVE steps 4 tig .. 4 tig + 3 of vehicle g: column c of tile A is step 4 (c >> 1) + (c & 1),
     // column c of tile B the step two later (the accumulator columns of a lane are 2 tig and 2 tig + 1).
-    // TAIL = the stage may reach past step T - 1 (identity steps, guarded stores) and holds the last
-    // step, whose values become the env's state; all other stages run without a single branch.
-    auto stage = [&](auto tail_tag, int k) {
+    // TAIL = the stage reaches past step T - 1 (only the last stage of a rollout whose length is not a
+    // multiple of 16): the missing steps are identity steps, TMA zero-fills their inputs and clips their
+    // output rows.
+    auto stage = [&](auto tail_tag, int k, LastStep& fin) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        if (lane == 0 && k + STAGES - 1 < NS) {  // refill the stage the previous iteration consumed
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(k + STAGES - 1);
-        }
         mbar_wait(bars + 8 * (k % STAGES), (uint32_t)(k / STAGES) & 1u);
         const unsigned char* st = ring_g + (k % STAGES) * STAGE_BYTES;
         // ---- cascaded reduction: B column g of tile A = row 4 (g >> 1) + (g & 1), of tile B two rows later
@@ -498,13 +526,18 @@ __global__ void __launch_bounds__(32, 16)
             dt[h] = __fmul2_rn(rate[h], f2(c.c_dt));
             dp[h] = __fmul2_rn(make_float2(cbrt_sfu(a1[h].x), cbrt_sfu(a1[h].y)), f2(c.c_dp));  // SARL:331
         }
-        bool ok[4];
+        // the inputs of this stage are in registers: its buffer can take the stage after next
+        __syncwarp();
+        if (lane == 0 && k + STAGES < NS) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(k + STAGES);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            ok[i] = !TAIL || tb + i < T;  // steps past the end of the rollout are identity steps (DataBuf >= 0)
+            const bool ok = !TAIL || tb + i < T;  // steps past the end of the rollout are identity steps (DataBuf >= 0)
             const float dti = (i & 1) ? dt[i >> 1].y : dt[i >> 1].x, dpi = (i & 1) ? dp[i >> 1].y : dp[i >> 1].x;
-            dd[i] = ok[i] ? __dadd_rn((double)dti, (double)dpi) : 0.0;
-            inc[i] = ok[i] ? __dmul_rn(__dmul_rn((double)arr[i], c.tf), 1000.0) : 0.0;
+            dd[i] = ok ? __dadd_rn((double)dti, (double)dpi) : 0.0;
+            inc[i] = ok ? __dmul_rn(__dmul_rn((double)arr[i], c.tf), 1000.0) : 0.0;
         }
         // ---- DataBuf at my first step: inclusive scan of the lanes' four-step maps over tig = 0..3
         MaxPlus f = mp_then(mp_then(MaxPlus{inc[0] - dd[0], inc[0]}, MaxPlus{inc[1] - dd[1], inc[1]}),
@@ -538,37 +571,39 @@ __global__ void __launch_bounds__(32, 16)
             cur = __dadd_rn(neg ? 0.0 : raw, inc[i]);          // SARL:354-356
             curf[i] = (float)cur;
         }
+        // ---- the out tile is free again once the TMA stores of the previous stage have read it
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
         float rew[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const float2 b = __fmul2_rn(make_float2(barg[2 * h], barg[2 * h + 1]), f2(c.c_rev));
             const float2 b3 = __fmul2_rn(__fmul2_rn(b, b), b);
             const float2 op = __fadd2_rn(a1[h], make_float2(-b3.x, -b3.y));  // SARL:336-339
-            const float2 base = __ffma2_rn(make_float2(nbf[2 * h], nbf[2 * h + 1]), f2(c.nt2),
-                                           __fmul2_rn(__fadd2_rn(a0[h], a1[h]), f2(c.nt1)));
+            const float2 base2 = __ffma2_rn(make_float2(nbf[2 * h], nbf[2 * h + 1]), f2(c.nt2),
+                                            __fmul2_rn(__fadd2_rn(a0[h], a1[h]), f2(c.nt1)));
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int i = 2 * h + u;
                 const float od = overd[i];
                 const float overp = od > 0.f ? (u ? op.y : op.x) : 0.f;  // only where the buffer went negative
                 const float pen = pos[i] ? c.pen1 : ((od > 2.0f) ? c.pen2 : 0.f);  // SARL:343-352
-                rew[i] = __fsub_rn(u ? base.y : base.x, pen);
-                if (ok[i]) {
-                    const unsigned oi = o_lane + (unsigned)(k * R + i) * sV;
-                    a.out.DataBuf[oi] = curf[i];
-                    a.out.data_t[oi] = u ? dt[h].y : dt[h].x;
-                    a.out.data_p[oi] = u ? dp[h].y : dp[h].x;
-                    a.out.over_power[oi] = overp;
-                    a.out.over_data[oi] = od;
-                    a.out.rate[oi] = u ? rate[h].y : rate[h].x;
-                    if (TAIL && tb + i == T - 1) {  // the reference object's attributes after the last step
-                        s.rate[ev] = u ? rate[h].y : rate[h].x;
-                        s.data_t[ev] = u ? dt[h].y : dt[h].x;
-                        s.data_p[ev] = u ? dp[h].y : dp[h].x;
-                        s.over_power[ev] = overp;
-                        s.over_data[ev] = od;
-                        s.data_r[ev] = arr[i];
-                    }
+                rew[i] = __fsub_rn(u ? base2.y : base2.x, pen);
+                float* o = out_w + 32 * i;
+                o[0 * TRACE_WORDS] = curf[i];
+                o[1 * TRACE_WORDS] = u ? dt[h].y : dt[h].x;
+                o[2 * TRACE_WORDS] = u ? dp[h].y : dp[h].x;
+                o[3 * TRACE_WORDS] = overp;
+                o[4 * TRACE_WORDS] = od;
+                o[5 * TRACE_WORDS] = u ? rate[h].y : rate[h].x;
+                if (TAIL ? (tb + i == T - 1) : (i == 3)) {  // dead code except in the rollout's last stage
+                    fin.rate = u ? rate[h].y : rate[h].x;
+                    fin.dt = u ? dt[h].y : dt[h].x;
+                    fin.dp = u ? dp[h].y : dp[h].x;
+                    fin.overp = overp;
+                    fin.overd = od;
+                    fin.arr = arr[i];
+                    fin.mine = TAIL ? true : (tig == 3);
                 }
             }
         }
@@ -580,22 +615,45 @@ __global__ void __launch_bounds__(32, 16)
             rew[i] += __shfl_xor_sync(kFull, rew[i], 16);
             rew[i] = __fmul_rn(rew[i], 0.125f);
         }
-        {  // every lane of a tig group holds the four means: lane g < 4 stores the one of step tb + g
+        {  // every lane of a tig group holds the four means: lane g < 4 files the one of step tb + g
             const float r01 = (g & 1) ? rew[1] : rew[0], r23 = (g & 1) ? rew[3] : rew[2];
             const float mine = (g & 2) ? r23 : r01;
-            if (g < 4 && (!TAIL || tb + g < T)) a.out.reward[r_lane + (unsigned)(k * R + g) * E] = mine;
-            if (TAIL && g < 4 && tb + g == T - 1) s.reward[e] = mine;
+            if (g < 4) out_r[4 * g] = mine;
+            if (TAIL ? (g < 4 && tb + g == T - 1) : (g == 3)) fin.rew = mine;
         }
-        __syncwarp();  // every lane is done with the stage before lane 0 re-arms it
+        // ---- out tile -> HBM: full 128-byte lines per (trace, step) for the block's four envs
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int n = 0; n < 6; ++n) tma_store_2d(&tm_out.trace[n], out_s + n * (TRACE_WORDS * 4), e0 * V, k * R);
+            tma_store_2d(&tm_out.reward, out_s + 6 * (TRACE_WORDS * 4), e0, k * R);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     };
-    for (int k = 0; k < NS - 1; ++k) stage(std::false_type{}, k);
-    stage(std::true_type{}, NS - 1);
+    LastStep fin{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0, false}, scratch = fin;
+    for (int k = 0; k < NS - 1; ++k) stage(std::false_type{}, k, scratch);
+    if (T % R == 0)
+        stage(std::false_type{}, NS - 1, fin);
+    else
+        stage(std::true_type{}, NS - 1, fin);
 
     // ---- registers -> state
     for (int m = lane; m < M; m += 32)  // elements_phase_shift_real = the last action_phase (SARL:128)
         s.phase_real[(size_t)e * M + m] = __ldg(a.phase + ((size_t)(T - 1) * E + e) * M + m);
+    if (fin.mine) {  // the reference object's attributes after the last step
+        s.rate[ev] = fin.rate;
+        s.data_t[ev] = fin.dt;
+        s.data_p[ev] = fin.dp;
+        s.over_power[ev] = fin.overp;
+        s.over_data[ev] = fin.overd;
+        s.data_r[ev] = fin.arr;
+    }
+    // the mean reward of step T - 1 sits in the lane (g = (T - 1) & 3, tig = ((T - 1) & 15) >> 2) that filed it
+    if (g == ((T - 1) & 3) && tig == (((T - 1) & 15) >> 2)) s.reward[e] = fin.rew;
     if (tig == 0) s.databuf[ev] = buf;
     if (lane == 0) s.step_ctr[e] += T;
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
 }
 
 }  // namespace risvec

@@ -24,7 +24,20 @@ import sys
 
 import numpy as _np
 
-REFERENCE_ROOT = os.environ.get("RISVEC_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """RISVEC_REFERENCE_ROOT, else the mounted tree (build container), else the git-ignored copy that
+    `tools/stage_reference.py` leaves under baseline/_ref (it travels to the GPU box with the snapshot)."""
+    env = os.environ.get("RISVEC_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    for cand in ("/root/reference", staged):
+        if os.path.isfile(os.path.join(cand, "Simulation-MARL-BCD", "Environment.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 _VARIANT_DIR = {"marl": "Simulation-MARL-BCD", "sarl": "Simulation-SARL"}
 
 # Lane constants used by both reference drivers

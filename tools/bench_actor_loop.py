@@ -50,6 +50,77 @@ class Actors(torch.nn.Module):
         return torch.softmax(logits.masked_fill(mask == 0, -1e9), dim=-1)
 
 
+def driver_loop(envs, steps, driver, actor_dtype, rank, world, local, ranks=None):
+    """One GPU's share of the loop (under torchrun: every rank its own shard, replicated actor weights);
+    returns the result dict (whole-job env-steps/s, device-timed, max over ranks)."""
+    torch.backends.cuda.matmul.allow_tf32 = actor_dtype == "tf32"
+    dev = torch.device("cuda", local)
+    E, V, M = envs, 8, 40
+    env = BatchedEnviron("marl", E, V, M, device=local, seed=1234, env_index_base=rank * E, **marl_yaml_overrides())
+    env.make_new_game(); env.renew_positions(); env.compute_parms(); env.optimize_phase_shift(); env.update_channel_gains()
+    part, ng = encode_groups([[0, 1], [2, 3], [4, 5], [6], [7]], V)
+    partner = torch.as_tensor(np.tile(part, (E, 1))).to(dev)
+    ngroups = torch.full((E,), ng, dtype=torch.int32, device=dev)
+    actors = Actors(V, dev)
+    if actor_dtype == "bf16":
+        actors = actors.to(torch.bfloat16)
+    obs = torch.empty(E, V, 5, device=dev)
+    obs2 = torch.empty(E, V, 5, device=dev)
+    if driver:
+        env.set_pairing(yaml=True)
+        env.pair_reset()
+        rb = ReplayBuffer(min(1_000_000, max(4 * E, 65536)), 5, V + 2, V, device=local)
+        K, q = mask_schedule(10, V, 7, 7, 0.10, 0.25, 200)
+        frozen = torch.ones(E, dtype=torch.int32, device=dev)
+        ctr = [0]
+
+    def driver_step():
+        first = ctr[0] % 100 == 0
+        ctr[0] += 1
+        env.observe(out=obs)
+        x = obs.to(torch.bfloat16) if actor_dtype == "bf16" else obs
+        raw = actors(x).float()
+        act = env.map_actions(raw)
+        part_v, ng_v = env.pair_noma(act, K, q, recalc_mask=first, reuse=None if first else frozen, new_episode=first)
+        probs = actors.intent(env.pair_mask)
+        env.step_marl(act, part_v, ng_v)
+        env.observe(out=obs2)
+        rb.store_marl(obs, probs, raw, env.reward, env.reward_user, obs2, done=(ctr[0] % 100 == 0),
+                      mask_u8=env.pair_mask)
+
+    def step():
+        if driver:
+            return driver_step()
+        env.observe(out=obs)
+        x = obs.to(torch.bfloat16) if actor_dtype == "bf16" else obs
+        act = env.map_actions(actors(x).float())
+        env.step_marl(act, partner, ngroups)  # arrivals: on-device Philox
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    if ranks is not None:
+        ranks.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    sec = t0.elapsed_time(t1) * 1e-3
+    if ranks is not None:
+        sec = ranks.max(sec)
+    res = {"envs_per_gpu": E, "V": V, "M": M, "steps": steps, "actor": "8 x MLP 5-512-256-{2, V} (bmm), " + actor_dtype,
+           "loop": ("observe, actors + intent head (torch), map_actions, NOMA pairing (solve on step 0 of each 100-step "
+                    "episode, frozen after), Environ.step (" + env.last_kernel() + "), observe, replay write")
+                   if driver else "observe, actors (torch), map_actions, Environ.step",
+           "value": world * E * steps / sec, "unit": "env-steps/s", "us_per_step": sec / steps * 1e6}
+    if driver:
+        res["replay_rows"] = int(rb.mem_cntr)
+        res["pairs_mean"] = float(env.noma_npairs.float().mean())
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=8192)

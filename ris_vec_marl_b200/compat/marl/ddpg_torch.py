@@ -52,5 +52,6 @@ class Agent:
 
     def load_models(self):
         path = os.path.join(model_dir(), f"actor_{self.agent_name}_ddpg")
-        self.actor.load_state_dict(torch.load(path, map_location=self.device))
+        # the checkpoints ship with the (untrusted) reference tree: tensors only, never unpickle code
+        self.actor.load_state_dict(torch.load(path, map_location=self.device, weights_only=True))
         self.actor.eval()

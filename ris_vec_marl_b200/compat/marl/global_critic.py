@@ -41,5 +41,7 @@ class Global_Critic:
 
     def load_models(self):
         for name, net in (("global_critic1_ddpg", self.global_critic1), ("global_critic2_ddpg", self.global_critic2)):
-            net.load_state_dict(torch.load(os.path.join(model_dir(), name), map_location=self.device))
+            # the checkpoints ship with the (untrusted) reference tree: tensors only, never unpickle code
+            net.load_state_dict(torch.load(os.path.join(model_dir(), name), map_location=self.device,
+                                           weights_only=True))
             net.eval()

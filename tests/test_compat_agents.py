@@ -29,7 +29,7 @@ def test_agent_and_global_critic_load_the_shipped_checkpoints(monkeypatch):
     gc.load_models()
     for a in agents:
         a.load_models()
-    sd = torch.load(os.path.join(MODELS, "actor_3_ddpg"), map_location="cpu")
+    sd = torch.load(os.path.join(MODELS, "actor_3_ddpg"), map_location="cpu", weights_only=True)
     assert torch.equal(agents[3].actor.mu.weight.detach().cpu(), sd["mu.weight"])
     np.random.seed(0)
     act = agents[3].choose_action([0.4, 0.1, 0.2, 0.0, 0.05])

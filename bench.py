@@ -366,7 +366,7 @@ def secondary_block(torch, ranks, args, rank, local, dev, peak):
         sec["config2_sarl_ab"] = {"error": repr(exc)[:200]}
     torch.cuda.empty_cache()
     try:  # config 4: 32 vehicles, 256 RIS elements, 1024 envs per GPU
-        E4, V4, M4, T4 = 1024, 32, 256, 64
+        E4, V4, M4, T4 = 1024, 32, 256, 256
         c4 = {"envs_per_gpu": E4, "V": V4, "M": M4, "T": T4}
         env, one, buf = make_rollout(torch, "sarl", E4, V4, M4, T4, local, rank, dev)
         c4["sarl_step"] = kernel_line(torch, ranks, "sarl", E4, V4, M4, T4, one, env, peak, n=5)

@@ -11,6 +11,7 @@
 #include "ris.cuh"
 #include "step.cuh"
 #include "sarl_mma.cuh"
+#include "sarl_mma_big.cuh"
 #include "pairing.cuh"
 #include "replay.cuh"
 
@@ -286,6 +287,32 @@ inline bool sarl_tma_covers(const risvec_env* env, const SarlArgs& a) {
            aligned16(o.data_p) && aligned16(o.over_power) && aligned16(o.over_data) && aligned16(o.rate) &&
            (uint64_t)a.T * env->dims.E * (M > 16 ? M : 16) < (1ull << 31);
 }
+// ---- many vehicles / elements (config 4): one block per env, k_sarl_mma_big
+template <int KQ>
+int launch_sarl_mma_big(risvec_env* env, const SarlArgs& a, cudaStream_t st, bool* launched) {
+    *launched = false;
+    const int E = env->dims.E, V = env->dims.V, T = a.T;
+    SarlBigOutMaps tm;
+    const risvec_sarl_out_t& o = a.out;
+    float* const traces[6] = {o.DataBuf, o.data_t, o.data_p, o.over_power, o.over_data, o.rate};
+    for (int n = 0; n < 6; ++n)
+        if (!tensor_map_2d(&tm.trace[n], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, traces[n], (uint64_t)E * V, T, V, 16))
+            return RISVEC_OK;  // not encodable: the caller falls back to the FP32-pipe kernels
+    auto kern = k_sarl_mma_big<KQ>;
+    const int smem = sarl_big_smem_bytes(KQ, V);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<E, kBigThreads, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm);
+    *launched = true;
+    return check_step_launch(env, "k_sarl_mma_big");
+}
+inline bool sarl_big_covers(const risvec_env* env, const SarlArgs& a) {
+    const risvec_sarl_out_t& o = a.out;
+    const int V = env->dims.V, M = env->dims.M;
+    return V % 4 == 0 && V <= 32 && M % 2 == 0 && M <= 256 && (V > 8 || M > 64) && o.DataBuf && o.data_t && o.data_p &&
+           o.over_power && o.over_data && o.rate && aligned16(o.DataBuf) && aligned16(o.data_t) && aligned16(o.data_p) &&
+           aligned16(o.over_power) && aligned16(o.over_data) && aligned16(o.rate) && (((uintptr_t)a.phase) & 7u) == 0 &&
+           (uint64_t)a.T * env->dims.E * (M > 2 * V ? M : 2 * V) < (1ull << 31);
+}
 inline bool sarl_mma_covers(const risvec_env* env) {
     return env->dims.V <= 8 && env->dims.M % 2 == 0 && env->dims.M <= 64;
 }
@@ -306,6 +333,13 @@ int launch_sarl(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
         if (M <= 24) return launch_sarl_mma<3>(env, a, st);
         if (M <= 40) return launch_sarl_mma<5>(env, a, st);
         return launch_sarl_mma<8>(env, a, st);
+    }
+    if ((path == kAuto || path == kMma) && a.in_rec == nullptr && sarl_big_covers(env, a) && env->sarl_tma) {
+        bool launched = false;
+        const int rc = M <= 64 ? launch_sarl_mma_big<2>(env, a, st, &launched)
+                               : (M <= 128 ? launch_sarl_mma_big<4>(env, a, st, &launched)
+                                           : launch_sarl_mma_big<8>(env, a, st, &launched));
+        if (rc != RISVEC_OK || launched) return rc;
     }
     if (VP <= 8 && M <= 40 && path != kGeneric)  // elements split over the env's 8 lanes (FP32 pipe)
         return M <= 16 ? launch_sarl_v8<2>(env, a, st) : launch_sarl_v8<5>(env, a, st);

@@ -361,7 +361,7 @@ struct SarlConsts {
     float c_rev;   // 1000 * L / time_fast * cbrt(k)      (SARL:318-319)
     float nt1, nt2;  // -t_factor1, -t_factor2            (SARL:341-352)
     float pen1, pen2;
-    float _pad;
+    float lam;     // Poisson arrival rate (on-device draws)
     double tf;     // time_fast
 };
 inline SarlConsts sarl_consts(const risvec_params_t& p) {
@@ -373,7 +373,7 @@ inline SarlConsts sarl_consts(const risvec_params_t& p) {
     c.nt2 = -(float)p.t_factor2;
     c.pen1 = (float)p.penalty1;
     c.pen2 = (float)p.penalty2;
-    c._pad = 0.f;
+    c.lam = (float)p.rate;
     c.tf = p.time_fast;
     return c;
 }

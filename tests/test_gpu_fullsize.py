@@ -34,15 +34,18 @@ def _sarl_env(path, E, V, M):
         return BatchedEnviron("sarl", E, V, M)
 
 
-# every SARL step kernel at BASELINE size: (path, M, kernel it must run)
-SARL_PATHS = [("mma", 40, "k_sarl_mma_tma"), ("mma-ldg", 40, "k_sarl_mma"), ("mma", 16, "k_sarl_mma_tma"),
-              ("mma", 24, "k_sarl_mma"), ("v8", 40, "k_sarl_v8"), ("packed", 40, "k_sarl_v8"),
-              ("generic", 40, "k_sarl_rollout"), ("generic", 64, "k_sarl_cascade2+k_sarl_scan")]
+# every SARL step kernel at BASELINE size: (path, V, M, E, kernel it must run)
+SARL_PATHS = [("mma", 8, 40, 4096, "k_sarl_mma_tma"), ("mma-ldg", 8, 40, 4096, "k_sarl_mma"),
+              ("mma", 8, 16, 4096, "k_sarl_mma_tma"), ("mma", 8, 24, 4096, "k_sarl_mma"), ("v8", 8, 40, 4096, "k_sarl_v8"),
+              ("packed", 8, 40, 4096, "k_sarl_v8"), ("generic", 8, 40, 4096, "k_sarl_rollout"),
+              ("generic", 8, 64, 4096, "k_sarl_cascade2+k_sarl_scan"),
+              ("mma", 32, 256, 1024, "k_sarl_mma_big"),                      # BASELINE config 4
+              ("generic", 32, 256, 1024, "k_sarl_cascade2+k_sarl_scan")]
 
 
-@pytest.mark.parametrize("path,M,kernel", SARL_PATHS, ids=[f"{p}-M{m}" for p, m, _ in SARL_PATHS])
-def test_sarl_4096_envs_rollout_matches_oracle(path, M, kernel):
-    E, V, T = 4096, 8, 32
+@pytest.mark.parametrize("path,V,M,E,kernel", SARL_PATHS, ids=[f"{p}-V{v}-M{m}" for p, v, m, _, _ in SARL_PATHS])
+def test_sarl_4096_envs_rollout_matches_oracle(path, V, M, E, kernel):
+    T = 32 if V == 8 else 24
     rng = np.random.default_rng(2024)
     ri = reset_draws(rng, E, V)
     mob = rng.random((E, 8 * V))

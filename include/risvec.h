@@ -176,6 +176,12 @@ int risvec_field(risvec_env_t* env, int field, void** dev_ptr, int64_t* rows, in
  * heading codes of the extra vehicles.  Both NULL -> on-device Philox draws. */
 int risvec_make_new_game(risvec_env_t* env, const int32_t* reset_ints, int n_ints, const int32_t* reset_dirs,
                          int n_dirs, void* stream);
+/* ... for a SUBSET of the envs: env_mask [E] u8 (device), != 0 = reset this env, 0 = leave every field of it
+ * untouched (a batched driver restarts the envs whose episode ended while the others run on; the reference
+ * object is one env, so its make_new_game is the all-ones mask).  NULL = all envs.  reset_ints / reset_dirs
+ * keep their [E, n] shape; rows of unmasked envs are ignored. */
+int risvec_make_new_game_masked(risvec_env_t* env, const uint8_t* env_mask, const int32_t* reset_ints, int n_ints,
+                                const int32_t* reset_dirs, int n_dirs, void* stream);
 
 /* renew_positions (MARL:412-542).  uniforms [E,n] f64 consumed per env by a cursor in the
  * reference's draw order (NULL -> Philox); used_out [E] i32 receives the draws consumed. */
@@ -308,6 +314,8 @@ int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float
                      void* stream);
 /* start of an episode (:1282-1297): history, streak, thresholds, mask and frozen groups cleared */
 int risvec_pair_reset(risvec_env_t* env, void* stream);
+/* ... for the envs with env_mask [E] u8 (device) != 0 only (NULL = all) */
+int risvec_pair_reset_masked(risvec_env_t* env, const uint8_t* env_mask, void* stream);
 
 /* ---- replay memory: Simulation-MARL-BCD/buffer.py, device resident ----
  * Same seven arrays as ReplayBuffer.__init__ (buffer.py:4-14): state / new_state [mem_size,
@@ -324,6 +332,7 @@ int risvec_replay_create(int device, int64_t mem_size, int input_shape, int n_ac
 int risvec_replay_destroy(risvec_replay_t* rb);
 int risvec_replay_field(risvec_replay_t* rb, int field, void** dev_ptr, int64_t* rows, int64_t* cols, int* elem_bytes);
 int64_t risvec_replay_count(const risvec_replay_t* rb); /* mem_cntr */
+int risvec_replay_set_count(risvec_replay_t* rb, int64_t mem_cntr); /* restore mem_cntr (checkpoint resume) */
 /* store_transition (buffer.py:16-25) for E transitions at once: transition e goes to slot
  * (mem_cntr + e) % mem_size, then mem_cntr += E.  All pointers device; done [E] u8 may be NULL
  * (then done_all applies to every row); mask_flat [E, n_agents^2] f32 may be NULL (all ones, the
@@ -349,6 +358,13 @@ int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* 
  * RISVEC_F_STATS columns and of RISVEC_F_REWARD, written (accumulate = 0) or added (accumulate != 0)
  * to out [RISVEC_NSTAT + 1] f64 (device). */
 int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream);
+
+/* Host-side call counters that key the on-device Philox draws of make_new_game, renew_positions and the channel /
+ * Random_phase draws (out / in = {reset, mobility, channel}).  Together with the RISVEC_F_* fields (which
+ * include step_ctr, the key of the arrival draws) and the params they are the whole state of a handle:
+ * a checkpoint that restores them continues the original random streams. */
+int risvec_get_rng_counters(const risvec_env_t* env, uint64_t out[3]);
+int risvec_set_rng_counters(risvec_env_t* env, const uint64_t in[3]);
 
 /* number of kernels this handle has launched so far (bench.py reports it as gpu_launches) */
 int64_t risvec_launch_count(const risvec_env_t* env);

@@ -117,6 +117,9 @@ EXPORTS = {
     "risvec_field": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "risvec_make_new_game": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "risvec_make_new_game_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                              C.c_void_p]),
+    "risvec_pair_reset_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "risvec_renew_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "risvec_compute_parms": (C.c_int, [C.c_void_p, C.c_void_p]),
     "risvec_set_phase": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -154,6 +157,9 @@ EXPORTS = {
     "risvec_replay_store_marl": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]),
     "risvec_replay_sample": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_void_p]),
     "risvec_shard_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "risvec_get_rng_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "risvec_set_rng_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "risvec_replay_set_count": (C.c_int, [C.c_void_p, C.c_int64]),
     "risvec_launch_count": (C.c_int64, [C.c_void_p]),
     "risvec_last_step_kernel": (C.c_char_p, [C.c_void_p]),
 }

@@ -189,14 +189,17 @@ class BatchedEnviron:
         return self._lib.risvec_last_step_kernel(self._h).decode()
 
     # ------------------------------------------------------------------ reference methods
-    def make_new_game(self, reset_ints=None, reset_dirs=None):
+    def make_new_game(self, reset_ints=None, reset_dirs=None, mask=None):
+        """`make_new_game` of every env, or -- `mask` [E] bool / u8 -- of the envs with mask != 0 only (the
+        others keep every field: per-env episode restarts of a batched driver)."""
         ri = self._dev(reset_ints, torch.int32)
         rd = self._dev(reset_dirs, torch.int32)
         n_i = 0 if ri is None else ri.shape[1]
         n_d = 0 if rd is None or rd.numel() == 0 else rd.shape[1]
         if rd is not None and rd.numel() == 0:
             rd = None
-        check(self._lib.risvec_make_new_game(self._h, self._p(ri), n_i, self._p(rd), n_d, self.stream))
+        mk = None if mask is None else self._dev(torch.as_tensor(mask).to(torch.uint8), torch.uint8, (self.E,))
+        check(self._lib.risvec_make_new_game_masked(self._h, self._p(mk), self._p(ri), n_i, self._p(rd), n_d, self.stream))
 
     def renew_positions(self, uniforms=None):
         u = self._dev(uniforms, torch.float64)
@@ -256,6 +259,18 @@ class BatchedEnviron:
             out[n] = torch.empty(shapes.get(n, (T, E, V)), dtype=torch.float32, device=self.device)
         return out
 
+    def _check_out(self, out, T, all_names):
+        """Preallocated traces go to the kernels as raw pointers: refuse anything that is not exactly the
+        buffer `_alloc_traces` would make (name, shape, float32, this device, contiguous)."""
+        shapes = {"reward": (T, self.E), "stats": (T, self.E, NSTAT), "last_power": (T, self.E, 2, self.V)}
+        for k, v in out.items():
+            if k not in all_names:
+                raise ValueError(f"unknown trace {k!r}")
+            want = shapes.get(k, (T, self.E, self.V))
+            if (not isinstance(v, torch.Tensor) or tuple(v.shape) != want or v.dtype != torch.float32
+                    or v.device != self.device or not v.is_contiguous()):
+                raise ValueError(f"out[{k!r}] must be a contiguous float32 tensor of shape {want} on {self.device}")
+
     def rollout_marl(self, actions, partner, ngroups, arrivals=None, traces=MARL_TRACES, out=None):
         """T fused Environ.step calls; actions [T,E,2,V]; returns {trace: tensor [T,...]}.
         `out` may hold preallocated trace tensors (as made by `_alloc_traces`)."""
@@ -268,6 +283,8 @@ class BatchedEnviron:
         ar = self._dev(arrivals, torch.int32, (T, self.E, self.V)) if arrivals is not None else None
         if out is None:
             out = self._alloc_traces(traces, T, MARL_TRACES)
+        else:
+            self._check_out(out, T, MARL_TRACES)
         o = MarlOut(**{k: v.data_ptr() for k, v in out.items()})
         check(self._lib.risvec_rollout_marl(self._h, T, self._p(a), self._p(pt), self._p(ng), self._p(ar), C.byref(o),
                                             self.stream))
@@ -282,6 +299,8 @@ class BatchedEnviron:
         ar = self._dev(arrivals, torch.int32, (T, self.E, self.V)) if arrivals is not None else None
         if out is None:
             out = self._alloc_traces(traces, T, SARL_TRACES)
+        else:
+            self._check_out(out, T, SARL_TRACES)
         o = SarlOut(**{k: v.data_ptr() for k, v in out.items()})
         check(self._lib.risvec_rollout_sarl(self._h, T, self._p(a), self._p(ph), self._p(ar), C.byref(o), self.stream))
         return out
@@ -413,9 +432,10 @@ class BatchedEnviron:
                 raise AttributeError(f"unknown pairing parameter {k!r}")
             setattr(self.pairing, k, type(getattr(self.pairing, k))(v))
 
-    def pair_reset(self):
-        """Start of an episode (marl_train_bcd.py:1282-1297)."""
-        check(self._lib.risvec_pair_reset(self._h, self.stream))
+    def pair_reset(self, mask=None):
+        """Start of an episode (marl_train_bcd.py:1282-1297); `mask` [E]: only the envs with mask != 0."""
+        mk = None if mask is None else self._dev(torch.as_tensor(mask).to(torch.uint8), torch.uint8, (self.E,))
+        check(self._lib.risvec_pair_reset_masked(self._h, self._p(mk), self.stream))
 
     def pair_noma(self, p01, topk, tau_q, recalc_mask=True, reuse=None, decay=True, new_episode=False):
         """One driver step of the pairing stage (marl_train_bcd.py:1315-1561) for every env.
@@ -447,8 +467,24 @@ class BatchedEnviron:
         return out
 
     def state_dict(self):
-        return {k: v.clone() for k, v in self._views.items()}
+        """Everything a resumed run needs to CONTINUE this one: the state arena, the host-side call counters
+        that key the on-device Philox draws, the scalar parameters and the pairing knobs."""
+        ctr = (C.c_uint64 * 3)()
+        check(self._lib.risvec_get_rng_counters(self._h, ctr))
+        sd = {k: v.clone() for k, v in self._views.items()}
+        sd["_rng_counters"] = [int(x) for x in ctr]
+        sd["_params"] = bytes(self.params)
+        sd["_pairing"] = bytes(self.pairing)
+        return sd
 
     def load_state_dict(self, sd):
         for k, v in sd.items():
-            self._views[k].copy_(v.to(self.device))
+            if not k.startswith("_"):
+                self._views[k].copy_(v.to(self.device))
+        if "_rng_counters" in sd:
+            check(self._lib.risvec_set_rng_counters(self._h, (C.c_uint64 * 3)(*sd["_rng_counters"])))
+        if "_params" in sd:
+            C.memmove(C.byref(self.params), sd["_params"], C.sizeof(Params))
+            check(self._lib.risvec_set_params(self._h, C.byref(self.params)))
+        if "_pairing" in sd:
+            C.memmove(C.byref(self.pairing), sd["_pairing"], C.sizeof(Pairing))

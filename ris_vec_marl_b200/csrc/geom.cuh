@@ -8,9 +8,11 @@ namespace risvec {
 
 // make_new_game: one thread per env (the draws of one env are consumed sequentially).
 __global__ void k_make_new_game(Dims d, State s, risvec_params_t p, const int* __restrict__ ints, int n_ints,
-                                const int* __restrict__ dirs, int n_dirs, unsigned long long call) {
+                                const int* __restrict__ dirs, int n_dirs, unsigned long long call,
+                                const unsigned char* __restrict__ env_mask) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= d.E) return;
+    if (env_mask != nullptr && env_mask[e] == 0) return;  // per-env reset: this env keeps its state
     const int V = d.V;
     int cur = 0, curd = 0;
     auto randint = [&](int lo, int hi) -> int {

@@ -496,14 +496,17 @@ __global__ void k_pair_noma(Dims d, State s, PairArgs a) {
 }
 
 // new episode (:1282-1297): history, streak, thresholds and frozen groups cleared
-__global__ void k_pair_reset(Dims d, PairArgs a) {
+__global__ void k_pair_reset(Dims d, PairArgs a, const unsigned char* __restrict__ env_mask) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int N = d.V, NN = N * N;
     if (t >= (long long)d.E * NN) return;
-    a.hist[t] = 0.f;
-    a.mask[t] = 0;
-    if (t < (long long)d.E * N) { a.streak[t] = 0; a.partner[t] = RISVEC_PARTNER_NONE; a.pairs[t] = -1; }
-    if (t < d.E) { a.tau[t] = 0.0; a.lastk[t] = 0; a.ngroups[t] = 0; a.npairs[t] = 0; a.rounds[t] = 0; }
+    auto on = [&](long long e) { return env_mask == nullptr || env_mask[e] != 0; };  // per-env reset
+    if (on(t / NN)) {
+        a.hist[t] = 0.f;
+        a.mask[t] = 0;
+    }
+    if (t < (long long)d.E * N && on(t / N)) { a.streak[t] = 0; a.partner[t] = RISVEC_PARTNER_NONE; a.pairs[t] = -1; }
+    if (t < d.E && on(t)) { a.tau[t] = 0.0; a.lastk[t] = 0; a.ngroups[t] = 0; a.npairs[t] = 0; a.rounds[t] = 0; }
 }
 
 }  // namespace risvec

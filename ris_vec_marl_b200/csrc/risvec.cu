@@ -35,6 +35,24 @@ int fail(int code, const char* fmt, ...) {
         if (_e != cudaSuccess) return fail(RISVEC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
+// Every entry point runs on the handle's device and then gives the caller its own current device back
+// (a single-process multi-GPU program must not find torch's current device changed by a library call).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+        else prev = -1;  // already current: nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ENTER_DEVICE(dev)        \
+    DeviceGuard _dev_guard(dev); \
+    if (!_dev_guard.ok) return fail(RISVEC_ERR_CUDA, "cudaSetDevice(%d) failed", (int)(dev))
+
 struct FieldDesc {
     size_t offset;
     int64_t rows, cols;
@@ -448,7 +466,7 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
     if (prop.major != 10)
         return fail(RISVEC_ERR_NODEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device,
                     prop.major, prop.minor);
-    CUDA_TRY(cudaSetDevice(device));
+    ENTER_DEVICE(device);
 
     risvec_env* env = new (std::nothrow) risvec_env();
     if (!env) return fail(RISVEC_ERR_INVALID, "out of host memory");
@@ -517,7 +535,7 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
 
 int risvec_destroy(risvec_env_t* env) {
     if (!env) return RISVEC_OK;
-    cudaSetDevice(env->device);
+    DeviceGuard _dev_guard(env->device);
     if (env->arena) cudaFree(env->arena);
     if (env->stage) cudaFree(env->stage);
     if (env->scratch) cudaFree(env->scratch);
@@ -558,6 +576,11 @@ int risvec_field(risvec_env_t* env, int field, void** dev_ptr, int64_t* rows, in
 
 int risvec_make_new_game(risvec_env_t* env, const int32_t* reset_ints, int n_ints, const int32_t* reset_dirs,
                          int n_dirs, void* stream) {
+    return risvec_make_new_game_masked(env, nullptr, reset_ints, n_ints, reset_dirs, n_dirs, stream);
+}
+
+int risvec_make_new_game_masked(risvec_env_t* env, const uint8_t* env_mask, const int32_t* reset_ints, int n_ints,
+                                const int32_t* reset_dirs, int n_dirs, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     const int V = env->dims.V;
     const int need = 9 * (V / 4) + 3 * (V % 4) + 1;
@@ -567,17 +590,17 @@ int risvec_make_new_game(risvec_env_t* env, const int32_t* reset_ints, int n_int
         return fail(RISVEC_ERR_INVALID, "reset_dirs needs %d headings per env", V % 4);
     if (reset_ints == nullptr && reset_dirs != nullptr)
         return fail(RISVEC_ERR_INVALID, "reset_dirs given without reset_ints");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     const int threads = 128, blocks = (env->dims.E + threads - 1) / threads;
     k_make_new_game<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, reset_ints, n_ints,
-                                                                  reset_dirs, n_dirs, env->reset_calls++);
+                                                                  reset_dirs, n_dirs, env->reset_calls++, env_mask);
     return check_launch(env, "k_make_new_game");
 }
 
 int risvec_renew_positions(risvec_env_t* env, const double* uniforms, int n, int32_t* used_out, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     if (uniforms != nullptr && n < 1) return fail(RISVEC_ERR_INVALID, "uniforms given with n = %d", n);
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     const int threads = 128, blocks = (env->dims.E + threads - 1) / threads;
     k_renew_positions<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, uniforms, n,
                                                                     used_out, env->mob_calls++);
@@ -586,7 +609,7 @@ int risvec_renew_positions(risvec_env_t* env, const double* uniforms, int n, int
 
 int risvec_compute_parms(risvec_env_t* env, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     const long long n = (long long)env->dims.E * env->dims.V;
     const int threads = 256, blocks = (int)((n + threads - 1) / threads);
     k_compute_parms<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st);
@@ -595,7 +618,7 @@ int risvec_compute_parms(risvec_env_t* env, void* stream) {
 
 int risvec_set_phase(risvec_env_t* env, const float* phase, void* stream) {
     if (!env || !phase) return fail(RISVEC_ERR_INVALID, "NULL argument");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     const long long n = (long long)env->dims.E * env->dims.M;
     const int threads = 256, blocks = (int)((n + threads - 1) / threads);
     k_set_phase<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, env->st, phase);
@@ -604,7 +627,7 @@ int risvec_set_phase(risvec_env_t* env, const float* phase, void* stream) {
 
 int risvec_optimize_phase_shift(risvec_env_t* env, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     if (env->dims.ncand <= 8 && env->dims.V <= 8 && env->dims.M <= 256 && !env->force_generic) {
         // 4 envs per warp, lane = (env, candidate)
         const int wpb = env->dims.M <= 64 ? 4 : 1;
@@ -626,7 +649,7 @@ int risvec_optimize_phase_shift(risvec_env_t* env, void* stream) {
 int risvec_update_channel_gains(risvec_env_t* env, const double* chan_rand, const double* chan_normal,
                                 const double* chan_exp, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     if (env->params.channel_model == RISVEC_CHANNEL_FREE) {
         if (!env->force_generic) {  // lane = (env, vehicle), sequential over the elements
             const int VP = pow2ceil(env->dims.V);
@@ -663,7 +686,7 @@ int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int
     if (env->dims.variant != RISVEC_VARIANT_MARL) return fail(RISVEC_ERR_INVALID, "handle is not a MARL env");
     if (T < 1) return fail(RISVEC_ERR_INVALID, "T must be >= 1 (got %d)", T);
     if (!action || !partner || !ngroups) return fail(RISVEC_ERR_INVALID, "action, partner and ngroups are required");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     MarlArgs a;
     memset(&a, 0, sizeof(a));
     a.T = T; a.action = action; a.partner = partner; a.ngroups = ngroups; a.arrivals = arrivals;
@@ -697,13 +720,15 @@ int risvec_rollout_sarl(risvec_env_t* env, int T, const float* action, const flo
     if (env->dims.variant != RISVEC_VARIANT_SARL) return fail(RISVEC_ERR_INVALID, "handle is not a SARL env");
     if (T < 1) return fail(RISVEC_ERR_INVALID, "T must be >= 1 (got %d)", T);
     if (!action || !phase) return fail(RISVEC_ERR_INVALID, "action and phase are required");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     SarlArgs a;
     memset(&a, 0, sizeof(a));
     a.T = T; a.action = action; a.phase = phase; a.arrivals = arrivals;
     if (out) a.out = *out;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (pow2ceil(env->dims.V)) {
+    int vp = pow2ceil(env->dims.V);
+    if (vp < 8 && env->dims.M > 40) vp = 8;  // few vehicles x many elements: 32 / VP envs per warp would not fit shared memory
+    switch (vp) {
         case 1: return launch_sarl<1>(env, a, st);
         case 2: return launch_sarl<2>(env, a, st);
         case 4: return launch_sarl<4>(env, a, st);
@@ -731,7 +756,7 @@ int risvec_rollout_sarl_packed(risvec_env_t* env, int T, const void* in_rec, flo
     if (!mpi)
         return fail(RISVEC_ERR_UNSUPPORTED, "packed SARL records need V == 8, E %% 4 == 0 and M in {16, 40} "
                     "(got V = %d, E = %d, M = %d)", env->dims.V, env->dims.E, env->dims.M);
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     SarlArgs a;
     memset(&a, 0, sizeof(a));
     a.T = T; a.in_rec = (const float*)in_rec; a.out_rec = out_rec; a.out.reward = reward;
@@ -747,7 +772,7 @@ int risvec_rollout_marl_packed(risvec_env_t* env, int T, const void* in_rec, con
     if (env->dims.V != 8 || env->dims.E % 4 != 0)
         return fail(RISVEC_ERR_UNSUPPORTED, "packed MARL records need V == 8 and E %% 4 == 0 (got V = %d, E = %d)",
                     env->dims.V, env->dims.E);
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     MarlArgs a;
     memset(&a, 0, sizeof(a));
     a.T = T; a.in_rec = (const float*)in_rec; a.partner = partner; a.ngroups = ngroups; a.out_rec = out_rec;
@@ -792,7 +817,7 @@ int risvec_rollout_marl_host(risvec_env_t* env, int T, const float* action, cons
                              void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     if (T < 1 || !action || !partner || !ngroups) return fail(RISVEC_ERR_INVALID, "bad arguments");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     if (int rc = ensure_pipe(env)) return rc;
     const size_t E = env->dims.E, V = env->dims.V, TE = (size_t)T * E;
     const size_t n_act = TE * 2 * V, n_ev = TE * V;
@@ -862,7 +887,7 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
                              const int32_t* arrivals, const risvec_sarl_out_t* out, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     if (T < 1 || !action || !phase) return fail(RISVEC_ERR_INVALID, "bad arguments");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     if (int rc = ensure_pipe(env)) return rc;
     const size_t E = env->dims.E, V = env->dims.V, M = env->dims.M, TE = (size_t)T * E;
     const size_t n_act = TE * 2 * V, n_ev = TE * V, n_ph = TE * M;
@@ -979,7 +1004,7 @@ int risvec_rollout_sarl_packed_host(risvec_env_t* env, int T, const void* in_rec
     if (T < 1 || !in_rec || !out_rec || !reward) return fail(RISVEC_ERR_INVALID, "bad arguments");
     if (!packed_sarl_mpi(env))
         return fail(RISVEC_ERR_UNSUPPORTED, "packed SARL records need V == 8, E %% 4 == 0 and M in {16, 40}");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     char* extra = nullptr;
     return packed_host_pipeline(env, T, RISVEC_SARL_IN_WORDS(env->dims.M), RISVEC_SARL_OUT_WORDS, in_rec, out_rec, reward,
                                 0, &extra, stream, [&](int tn, const float* di, float* dout, float* dr) {
@@ -993,7 +1018,7 @@ int risvec_rollout_marl_packed_host(risvec_env_t* env, int T, const void* in_rec
     if (T < 1 || !in_rec || !partner || !ngroups || !out_rec || !reward) return fail(RISVEC_ERR_INVALID, "bad arguments");
     if (env->dims.V != 8 || env->dims.E % 4 != 0)
         return fail(RISVEC_ERR_UNSUPPORTED, "packed MARL records need V == 8 and E %% 4 == 0");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     if (int rc = ensure_pipe(env)) return rc;
     const size_t E = env->dims.E;
     char* extra = nullptr;
@@ -1013,7 +1038,7 @@ int risvec_rollout_marl_packed_host(risvec_env_t* env, int T, const void* in_rec
 
 int risvec_observe(risvec_env_t* env, float* obs, void* stream) {
     if (!env || !obs) return fail(RISVEC_ERR_INVALID, "NULL argument");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     const int n_theta = env->dims.variant == RISVEC_VARIANT_SARL ? env->dims.M / env->dims.V : 0;
     const long long n = (long long)env->dims.E * env->dims.V;
     k_observe<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, obs, n_theta);
@@ -1022,7 +1047,7 @@ int risvec_observe(risvec_env_t* env, float* obs, void* stream) {
 
 int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float* phase, void* stream) {
     if (!env || !raw || !action) return fail(RISVEC_ERR_INVALID, "NULL argument");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     const Dims& d = env->dims;
     if (d.variant == RISVEC_VARIANT_MARL) {
         const long long n = (long long)d.E * d.V;
@@ -1037,7 +1062,7 @@ int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float
 
 int risvec_random_phase(risvec_env_t* env, const int32_t* idx, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     const long long n = (long long)env->dims.E * env->dims.M;
     k_random_phase<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, idx, env->chan_calls++);
     return check_launch(env, "k_random_phase");
@@ -1046,7 +1071,7 @@ int risvec_random_phase(risvec_env_t* env, const int32_t* idx, void* stream) {
 int risvec_direct_link(risvec_env_t* env, const double* normals, double* path_loss, double* shadowing, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     if (!path_loss && !shadowing) return fail(RISVEC_ERR_INVALID, "both outputs are NULL");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     const long long n = (long long)env->dims.E * env->dims.V;
     const double* shadow_state = (const double*)(env->arena + env->fields[RISVEC_F_V2I_SHADOWING].offset);
     k_direct_link<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->dims, env->st, env->params, shadow_state,
@@ -1115,7 +1140,7 @@ int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float
                     RISVEC_PAIR_MAX_V);
     if (p01_env_stride < V) return fail(RISVEC_ERR_INVALID, "p01_env_stride %lld < V", (long long)p01_env_stride);
     if (!(tau_q >= 0.0 && tau_q <= 1.0)) return fail(RISVEC_ERR_INVALID, "tau_q must be in [0, 1]");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     PairArgs a = pair_state_args(env);
     a.p01 = p01; a.p01_stride = p01_env_stride; a.reuse = reuse;
     a.topk = topk; a.tau_q = tau_q; a.recalc = recalc_mask != 0; a.decay = decay != 0; a.fresh = new_episode != 0;
@@ -1144,13 +1169,15 @@ int risvec_pair_noma(risvec_env_t* env, const risvec_pairing_t* cfg, const float
     return check_launch(env, "k_pair_noma");
 }
 
-int risvec_pair_reset(risvec_env_t* env, void* stream) {
+int risvec_pair_reset(risvec_env_t* env, void* stream) { return risvec_pair_reset_masked(env, nullptr, stream); }
+
+int risvec_pair_reset_masked(risvec_env_t* env, const uint8_t* env_mask, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     PairArgs a = pair_state_args(env);
     const long long n = (long long)env->dims.E * env->dims.V * env->dims.V;
     const int threads = 256, blocks = (int)((n + threads - 1) / threads);
-    k_pair_reset<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, a);
+    k_pair_reset<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->dims, a, env_mask);
     return check_launch(env, "k_pair_reset");
 }
 
@@ -1166,7 +1193,7 @@ int risvec_replay_create(int device, int64_t mem_size, int input_shape, int n_ac
         return fail(RISVEC_ERR_NODEVICE, "no CUDA device visible: this library has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return fail(RISVEC_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
-    CUDA_TRY(cudaSetDevice(device));
+    ENTER_DEVICE(device);
     risvec_replay* rb = new (std::nothrow) risvec_replay();
     if (!rb) return fail(RISVEC_ERR_INVALID, "out of host memory");
     memset(rb, 0, sizeof(*rb));
@@ -1198,7 +1225,7 @@ int risvec_replay_create(int device, int64_t mem_size, int input_shape, int n_ac
 
 int risvec_replay_destroy(risvec_replay_t* rb) {
     if (!rb) return RISVEC_OK;
-    cudaSetDevice(rb->device);
+    DeviceGuard _dev_guard(rb->device);
     if (rb->base) cudaFree(rb->base);
     delete rb;
     return RISVEC_OK;
@@ -1217,6 +1244,11 @@ int risvec_replay_field(risvec_replay_t* rb, int field, void** dev_ptr, int64_t*
 }
 
 int64_t risvec_replay_count(const risvec_replay_t* rb) { return rb ? rb->mem_cntr : 0; }
+int risvec_replay_set_count(risvec_replay_t* rb, int64_t mem_cntr) {
+    if (!rb || mem_cntr < 0) return fail(RISVEC_ERR_INVALID, "NULL handle or negative count");
+    rb->mem_cntr = mem_cntr;
+    return RISVEC_OK;
+}
 
 static int replay_store(risvec_replay* rb, int E, const ReplaySrc& src, int marl, cudaStream_t st) {
     const ReplayMem& m = rb->m;
@@ -1244,7 +1276,7 @@ int risvec_replay_store(risvec_replay_t* rb, int E, const float* state, const fl
                         const float* mask_flat, void* stream) {
     if (!rb || !state || !action || !reward_g || !reward_l || !state_) return fail(RISVEC_ERR_INVALID, "NULL argument");
     if (E < 1 || E > rb->m.mem_size) return fail(RISVEC_ERR_INVALID, "E = %d must be in [1, mem_size]", E);
-    CUDA_TRY(cudaSetDevice(rb->device));
+    ENTER_DEVICE(rb->device);
     ReplaySrc src;
     memset(&src, 0, sizeof(src));
     src.state = state; src.state_ = state_; src.action = action; src.reward_g = reward_g; src.reward_l = reward_l;
@@ -1261,7 +1293,7 @@ int risvec_replay_store_marl(risvec_replay_t* rb, int E, const float* state, con
     if (E < 1 || E > rb->m.mem_size) return fail(RISVEC_ERR_INVALID, "E = %d must be in [1, mem_size]", E);
     if (rb->m.A != rb->m.N * (rb->m.N + 2))
         return fail(RISVEC_ERR_INVALID, "store_marl needs n_actions = n_agents + 2 (got %d per agent)", rb->m.A / rb->m.N);
-    CUDA_TRY(cudaSetDevice(rb->device));
+    ENTER_DEVICE(rb->device);
     ReplaySrc src;
     memset(&src, 0, sizeof(src));
     src.state = state; src.state_ = state_; src.probs = intent_probs; src.power = power_raw; src.reward_g = reward_g;
@@ -1275,7 +1307,7 @@ int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* 
     if (!rb || !idx || !states || !actions || !rewards_g || !rewards_l || !states_ || !dones || !masks)
         return fail(RISVEC_ERR_INVALID, "NULL argument");
     if (B < 1) return fail(RISVEC_ERR_INVALID, "B must be >= 1");
-    CUDA_TRY(cudaSetDevice(rb->device));
+    ENTER_DEVICE(rb->device);
     k_replay_sample<<<B, 128, 0, (cudaStream_t)stream>>>(rb->m, B, (const long long*)idx, states, actions, rewards_g,
                                                         rewards_l, states_, dones, masks);
     cudaError_t e = cudaGetLastError();
@@ -1286,7 +1318,7 @@ int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* 
 
 int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream) {
     if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
-    CUDA_TRY(cudaSetDevice(env->device));
+    ENTER_DEVICE(env->device);
     if (!accumulate) CUDA_TRY(cudaMemsetAsync(out, 0, (RISVEC_NSTAT + 1) * sizeof(double), (cudaStream_t)stream));
     int blocks = (env->dims.E + 63) / 64;   // 64 envs per block and pass; at most one block per SM
     if (blocks > 148) blocks = 148;
@@ -1294,6 +1326,16 @@ int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* str
     return check_launch(env, "k_shard_stats");
 }
 
+int risvec_get_rng_counters(const risvec_env_t* env, uint64_t out[3]) {
+    if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    out[0] = env->reset_calls; out[1] = env->mob_calls; out[2] = env->chan_calls;
+    return RISVEC_OK;
+}
+int risvec_set_rng_counters(risvec_env_t* env, const uint64_t in[3]) {
+    if (!env || !in) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    env->reset_calls = in[0]; env->mob_calls = in[1]; env->chan_calls = in[2];
+    return RISVEC_OK;
+}
 int64_t risvec_launch_count(const risvec_env_t* env) { return env ? env->launches : 0; }
 const char* risvec_last_step_kernel(const risvec_env_t* env) { return (env && env->step_kernel) ? env->step_kernel : ""; }
 

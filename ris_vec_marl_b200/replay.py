@@ -38,6 +38,14 @@ class ReplayBuffer:
     def mem_cntr(self):
         return int(self._lib.risvec_replay_count(self._h))
 
+    def state_dict(self):
+        return {**{n: getattr(self, n).clone() for n in REPLAY_FIELDS}, "_mem_cntr": self.mem_cntr}
+
+    def load_state_dict(self, sd):
+        for n in REPLAY_FIELDS:
+            getattr(self, n).copy_(sd[n].to(self.device))
+        check(self._lib.risvec_replay_set_count(self._h, int(sd["_mem_cntr"])))
+
     @property
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

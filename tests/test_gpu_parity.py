@@ -351,3 +351,73 @@ def test_checkpoint_roundtrip_and_attribute_writes():
     assert torch.equal(got2["rate"], ref["rate"]) and not torch.equal(got2["reward_user"], ref["reward_user"])
     want = -(2.0 * b.stats[:, 0])  # reward = -(w_d * delay) when w_e = 0 and no QoS penalty
     np.testing.assert_allclose(b.reward.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_resumed_run_continues_the_random_streams():
+    """A run that is checkpointed, loaded into a FRESH handle (default parameters, counters at zero) and
+    resumed must equal the uninterrupted run: the on-device Philox draws of renew_positions and make_new_game
+    are keyed by host-side call counters, which `state_dict` carries along with the params and the arena."""
+    from ris_vec_marl_b200 import BatchedEnviron, ReplayBuffer, marl_yaml_overrides
+
+    E, V, M, T = 32, 8, 40, 6
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    acts = torch.rand(3 * T, E, 2, V, device="cuda", generator=gen)
+    part = torch.full((E, V), -1, dtype=torch.int32, device="cuda")
+    ng = torch.full((E,), V, dtype=torch.int32, device="cuda")
+
+    def episode(env, k):
+        env.renew_positions(); env.compute_parms(); env.optimize_phase_shift(); env.update_channel_gains()
+        return env.rollout_marl(acts[k * T:(k + 1) * T], part, ng)
+
+    whole = BatchedEnviron("marl", E, V, M, seed=11, **marl_yaml_overrides())
+    whole.make_new_game()
+    ref = [episode(whole, k) for k in range(3)]
+    first = BatchedEnviron("marl", E, V, M, seed=11, **marl_yaml_overrides())
+    first.make_new_game()
+    episode(first, 0)
+    sd = first.state_dict()
+    resumed = BatchedEnviron("marl", E, V, M, seed=11)  # NOT given the yaml overrides: they come from the checkpoint
+    resumed.load_state_dict(sd)
+    for k in (1, 2):
+        got = episode(resumed, k)
+        for name in ref[k]:
+            assert torch.equal(ref[k][name], got[name]), (k, name)
+    assert torch.equal(whole.pos_x, resumed.pos_x) and torch.equal(whole.DataBuf, resumed.DataBuf)
+    # replay memory: mem_cntr travels with the arrays
+    rb = ReplayBuffer(64, 5, V + 2, V)
+    st = torch.rand(8, V * 5, device="cuda")
+    rb.store_transitions(st, torch.rand(8, V * (V + 2), device="cuda"), torch.rand(8, device="cuda"),
+                         torch.rand(8, V, device="cuda"), st, False)
+    rb2 = ReplayBuffer(64, 5, V + 2, V)
+    rb2.load_state_dict(rb.state_dict())
+    assert rb2.mem_cntr == rb.mem_cntr == 8 and torch.equal(rb2.state_memory, rb.state_memory)
+
+
+def test_masked_reset_touches_only_the_selected_envs():
+    """risvec_make_new_game_masked / risvec_pair_reset_masked: envs outside the mask keep every field."""
+    from ris_vec_marl_b200 import BatchedEnviron, marl_yaml_overrides
+
+    E, V, M = 64, 8, 40
+    rng = np.random.default_rng(5)
+    pat = [(0, 4), (220, 230), (10, 15), (170, 180), (10, 15), (220, 230), (10, 15), (170, 180), (10, 15)] * (V // 4) + [(5, 9)]
+    ri = np.stack([rng.integers(lo, hi, E) for lo, hi in pat], axis=1).astype(np.int32)
+    env = BatchedEnviron("marl", E, V, M, seed=2, **marl_yaml_overrides())
+    env.make_new_game(); env.renew_positions(); env.compute_parms(); env.optimize_phase_shift(); env.update_channel_gains()
+    env.rollout_marl(torch.rand(5, E, 2, V, device="cuda"), torch.full((E, V), -1, dtype=torch.int32, device="cuda"),
+                     torch.full((E,), V, dtype=torch.int32, device="cuda"))
+    env.pair_hist.fill_(0.25)
+    before = {k: env.state(k).clone() for k in ("pos_x", "pos_y", "dir", "vel", "DataBuf", "pair_hist", "noma_ngroups")}
+    mask = torch.zeros(E, dtype=torch.bool, device="cuda")
+    mask[::3] = True
+    env.make_new_game(ri, mask=mask)
+    env.pair_reset(mask=mask)
+    full = BatchedEnviron("marl", E, V, M, seed=2, **marl_yaml_overrides())
+    full.make_new_game(ri)
+    for k in ("pos_x", "pos_y", "dir", "vel", "DataBuf"):
+        assert torch.equal(env.state(k)[~mask], before[k][~mask]), k          # untouched
+        assert torch.equal(env.state(k)[mask], full.state(k)[mask]), k        # exactly a reset with the same draws
+    assert torch.equal(env.pair_hist[~mask], before["pair_hist"][~mask]) and (env.pair_hist[mask] == 0).all()
+    with pytest.raises(ValueError):  # preallocated traces are validated before their pointers reach a kernel
+        env.rollout_marl(torch.rand(5, E, 2, V, device="cuda"), torch.full((E, V), -1, dtype=torch.int32, device="cuda"),
+                         torch.full((E,), V, dtype=torch.int32, device="cuda"),
+                         out={"rate": torch.empty(4, E, V, device="cuda")})

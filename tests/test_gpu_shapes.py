@@ -10,7 +10,8 @@ from tests.parity import RTOL, sarl_rate_atol, sarl_reward_band
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1, 1), (3, 2), (2, 17), (8, 16), (8, 24), (16, 63), (9, 129), (17, 100), (31, 255), (32, 512), (5, 1024),
-          (4, 100), (12, 200), (20, 66), (32, 256), (8, 130),   # k_sarl_mma_big (V % 4 == 0, M even, M <= 256)
+          (4, 100), (12, 200), (20, 66), (32, 256), (8, 130),   # k_sarl_mma_big
+          (4, 1024), (2, 512), (1, 256),                        # few vehicles x many elements (8-lane mapping) (V % 4 == 0, M even, M <= 256)
           (32, 1024)]     # the last one is the largest shape the library accepts
 
 

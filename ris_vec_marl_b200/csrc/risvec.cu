@@ -12,6 +12,7 @@
 #include "step.cuh"
 #include "sarl_mma.cuh"
 #include "sarl_mma_big.cuh"
+#include "marl_tma.cuh"
 #include "pairing.cuh"
 #include "replay.cuh"
 
@@ -89,6 +90,7 @@ struct risvec_env {
     int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
     int sarl_path;      // RISVEC_SARL_PATH = auto (0) | mma (1) | v8 (2) | generic (3): tests / A-B runs
     int sarl_tma;       // RISVEC_SARL_TMA = 0 keeps the mma path on its LDG kernel (tests / A-B runs)
+    int marl_tma;       // RISVEC_MARL_PATH = v8 keeps the MARL fast path on k_marl_v8 (tests / A-B runs)
     const char* step_kernel;  // name of the kernel(s) the latest rollout launched (risvec_last_step_kernel)
 };
 
@@ -479,6 +481,8 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
         const char* sp = getenv("RISVEC_SARL_PATH");
         env->sarl_path = !sp ? 0 : (!strcmp(sp, "mma") ? 1 : (!strcmp(sp, "v8") ? 2 : (!strcmp(sp, "generic") ? 3 : 0)));
         env->step_kernel = "";
+        const char* mp = getenv("RISVEC_MARL_PATH");
+        env->marl_tma = !(mp != nullptr && !strcmp(mp, "v8"));
         const char* tm = getenv("RISVEC_SARL_TMA");
         env->sarl_tma = !(tm != nullptr && tm[0] == '0');
         if (sp && !strcmp(sp, "mma-ldg")) {  // the tensor-core path without the TMA staging
@@ -697,6 +701,29 @@ int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int
         const risvec_marl_out_t& o = a.out;
         const bool full = arrivals && o.reward_user && o.reward && o.DataBuf && o.data_t && o.data_p && o.rate &&
                           !o.over_power;
+        // BASELINE shape: the time-parallel kernel (one warp per env, TMA in / out); RISVEC_MARL_PATH=v8 pins the old one
+        if (full && env->marl_tma && env->dims.V == 8 && env->dims.E % 4 == 0 && aligned16(action) && aligned16(arrivals) &&
+            aligned16(o.reward_user) && aligned16(o.reward) && aligned16(o.DataBuf) && aligned16(o.data_t) &&
+            aligned16(o.data_p) && aligned16(o.rate) && (uint64_t)T * env->dims.E * 16 < (1ull << 31)) {
+            const int E = env->dims.E, V = 8;
+            CUtensorMap tm_ac, tm_ar;
+            MarlOutMaps tm;
+            float* const traces[5] = {o.reward_user, o.DataBuf, o.data_t, o.data_p, o.rate};
+            bool ok = tensor_map_2d(&tm_ac, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, action, (uint64_t)E * 2 * V, T, 2 * V, 16) &&
+                      tensor_map_2d(&tm_ar, CU_TENSOR_MAP_DATA_TYPE_INT32, arrivals, (uint64_t)E * V, T, V, 16) &&
+                      tensor_map_2d(&tm.reward, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, o.reward, (uint64_t)E, T, 4, 16);
+            for (int n = 0; n < 5 && ok; ++n)
+                ok = tensor_map_2d(&tm.trace[n], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, traces[n], (uint64_t)E * V, T, 4 * V, 16);
+            if (ok) {
+                static bool attr_set = false;
+                if (!attr_set) {
+                    CUDA_TRY(cudaFuncSetAttribute(k_marl_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMarlSmemBytes));
+                    attr_set = true;
+                }
+                k_marl_tma<<<E / 4, 128, kMarlSmemBytes, st>>>(env->dims, env->st, marl_consts(env->params), a, tm_ac, tm_ar, tm);
+                return check_step_launch(env, "k_marl_tma");
+            }
+        }
         const int warps = (env->dims.E + 3) / 4;
         if (full)
             k_marl_v8<true, false><<<warps, 32, 0, st>>>(env->dims, env->st, env->params, a);

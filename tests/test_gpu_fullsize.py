@@ -94,10 +94,14 @@ def test_sarl_4096_envs_rollout_matches_oracle(path, V, M, E, kernel):
     assert np.all((got["over_data"] > 0) <= (got["DataBuf"] - arr <= 1e-6))  # overflow only when the buffer drained
 
 
-def test_marl_4096_envs_rollout_matches_oracle():
+@pytest.mark.parametrize("path,kernel,T", [("tma", "k_marl_tma", 40), ("tma", "k_marl_tma", 32), ("v8", "k_marl_v8", 12)])
+def test_marl_4096_envs_rollout_matches_oracle(path, kernel, T):
+    import os
+
     from ris_vec_marl_b200 import BatchedEnviron, marl_yaml_overrides
 
-    E, V, M, T = 4096, 8, 40, 12
+    E, V, M = 4096, 8, 40
+    os.environ["RISVEC_MARL_PATH"] = path  # read when the handle is created
     rng = np.random.default_rng(77)
     ri = reset_draws(rng, E, V)
     mob = rng.random((E, 8 * V))
@@ -107,13 +111,17 @@ def test_marl_4096_envs_rollout_matches_oracle():
     part, ng = encode_groups([[0, 1], [3, 2], [4, 5], [6], [7]], V)
     partner, ngroups = np.tile(part, (E, 1)), np.full(E, ng, dtype=np.int32)
 
-    env = BatchedEnviron("marl", E, V, M, **marl_yaml_overrides())
+    try:
+        env = BatchedEnviron("marl", E, V, M, **marl_yaml_overrides())
+    finally:
+        os.environ.pop("RISVEC_MARL_PATH", None)
     env.make_new_game(ri); env.renew_positions(mob); env.compute_parms()
     phase0 = np.zeros((E, M), dtype=np.float32)
     env.get_next_phase(phase0)  # theta = 1: includes destructive-interference gains
     env.update_channel_gains()
     got = {k: v.cpu().numpy() for k, v in env.rollout_marl(
         acts, partner, ngroups, arr, traces=("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate")).items()}
+    assert env.last_kernel() == kernel, (env.last_kernel(), kernel)
 
     d = InjectedDraws(reset_ints=ri, arrivals=arr)
     o = EnvOracle("marl", V, M, 3, E=E, params=OracleParams.marl_yaml(), draws=d)
@@ -135,4 +143,14 @@ def test_marl_4096_envs_rollout_matches_oracle():
         close(got["reward_user"][t], r_user, 2e-6, f"reward_user t={t}", mask=band)
         close(got["reward"][t], r_glob, 2e-6, f"reward t={t}", mask=band.any(axis=1))
     np.testing.assert_allclose(env.mec_queue_cycles.cpu().numpy(), o.mec_queue_cycles, rtol=1e-6, atol=1.0)
+    # the state after the rollout is the last step's (`last_*` statistics included)
+    np.testing.assert_allclose(env.DataBuf.cpu().numpy(), o.DataBuf, rtol=RTOL, atol=1e-5)
+    st = env.stats.cpu().numpy()
+    amp_env = amp | band.any(axis=1)
+    close(st[:, 0], L["delay_mean"], 1e-9, "last_delay_mean", mask=amp_env)
+    close(st[:, 1], L["energy_mean"], 1e-9, "last_energy_mean")
+    close(st[:, 6], L["backlog_kbit_mean"], 1e-5, "last_backlog_kbit_mean")
+    close(st[:, 10], L["off_kbit_sum"], 1e-5, "last_off_kbit_sum")
+    close(st[:, 11], L["local_kbit_sum"], 1e-5, "last_local_kbit_sum")
+    close(env.reward.cpu().numpy(), r_glob, 2e-6, "state reward", mask=band.any(axis=1))
     assert (got["DataBuf"] >= 0).all() and (got["rate"] >= 0).all() and (np.abs(got["reward_user"]) <= 50).all()

@@ -110,6 +110,76 @@ __global__ void k_replay_store(ReplayMem m, long long first, int E, ReplaySrc sr
     }
 }
 
+// float4 form of the same store without per-element row arithmetic: blockIdx.y selects the field; because
+// the E rows land in consecutive ring slots, every field is a FLAT copy of E * width floats whose
+// destination is contiguous up to one wrap of the ring (n_wrap = rows before the wrap).  Only the assembled
+// MARL action rows need a row index (one 32-bit division per 16 bytes).
+template <int MARL>
+__global__ void __launch_bounds__(256) k_replay_store_flat(ReplayMem m, long long slot0, int n_wrap, int E, ReplaySrc src) {
+    const int N = m.N, NN = N * N, AW = N + 2;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    auto flat_copy = [&](float* dst_field, const float* src_field, int W) {  // W floats per row, W % 4 == 0
+        const unsigned n4 = (unsigned)E * (W / 4), w4 = (unsigned)n_wrap * (W / 4);
+        float4* d0 = reinterpret_cast<float4*>(dst_field + slot0 * W);
+        float4* d1 = reinterpret_cast<float4*>(dst_field);
+        const float4* sp = reinterpret_cast<const float4*>(src_field);
+        for (unsigned i = tid; i < n4; i += nthr) {
+            const float4 v = __ldg(sp + i);
+            if (i < w4) d0[i] = v;
+            else d1[i - w4] = v;
+        }
+    };
+    switch (blockIdx.y) {
+        case 0: flat_copy(m.state, src.state, m.S); break;
+        case 1: flat_copy(m.state_, src.state_, m.S); break;
+        case 2: flat_copy(m.reward_l, src.reward_l, N); break;
+        case 3: {
+            if (!MARL) { flat_copy(m.action, src.action, m.A); break; }
+            const unsigned rw = m.A / 4, n4 = (unsigned)E * rw, w4 = (unsigned)n_wrap * rw;
+            float4* d0 = reinterpret_cast<float4*>(m.action + slot0 * m.A);
+            float4* d1 = reinterpret_cast<float4*>(m.action);
+            for (unsigned i = tid; i < n4; i += nthr) {
+                const unsigned e = i / rw, c = i - e * rw;
+                float o[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {  // row = per agent [intent probs (N, diagonal zeroed) | raw power (2)]
+                    const int col = (int)c * 4 + x, a = col / AW, k = col - a * AW;
+                    o[x] = k < N ? (k == a ? 0.f : __ldg(src.probs + ((size_t)e * N + a) * N + k))
+                                 : __ldg(src.power + ((size_t)e * N + a) * 2 + (k - N));
+                }
+                const float4 v = make_float4(o[0], o[1], o[2], o[3]);
+                if (i < w4) d0[i] = v;
+                else d1[i - w4] = v;
+            }
+            break;
+        }
+        case 4: {
+            const unsigned n4 = (unsigned)E * (NN / 4), w4 = (unsigned)n_wrap * (NN / 4);
+            float4* d0 = reinterpret_cast<float4*>(m.mask + slot0 * NN);
+            float4* d1 = reinterpret_cast<float4*>(m.mask);
+            const float4* sf = reinterpret_cast<const float4*>(src.mask_f);
+            const uchar4* su = reinterpret_cast<const uchar4*>(src.mask_u8);
+            for (unsigned i = tid; i < n4; i += nthr) {
+                float4 v = make_float4(1.f, 1.f, 1.f, 1.f);  // no mask supplied: all ones (marl_train_bcd.py:1786-1789)
+                if (MARL) {
+                    if (su) { const uchar4 b = __ldg(su + i); v = make_float4(b.x, b.y, b.z, b.w); }
+                } else if (sf) {
+                    v = __ldg(sf + i);
+                }
+                if (i < w4) d0[i] = v;
+                else d1[i - w4] = v;
+            }
+            break;
+        }
+        default:
+            for (unsigned u = tid; u < (unsigned)E; u += nthr) {  // reward_global, terminal
+                const long long slot = (int)u < n_wrap ? slot0 + u : (long long)u - n_wrap;
+                m.reward_g[slot] = src.reward_g[u];
+                m.terminal[slot] = src.done ? (src.done[u] != 0) : (src.done_all != 0);
+            }
+    }
+}
+
 // sample_buffer (buffer.py:27-39) for caller-drawn indices: one block per sampled row
 __global__ void k_replay_sample(ReplayMem m, int B, const long long* __restrict__ idx, float* __restrict__ states,
                                 float* __restrict__ actions, float* __restrict__ rewards_g,

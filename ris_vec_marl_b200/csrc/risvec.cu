@@ -1287,7 +1287,18 @@ static int replay_store(risvec_replay* rb, int E, const ReplaySrc& src, int marl
     const int threads = 256;
     long long blocks = (total + threads - 1) / threads;
     if (blocks > 148 * 64) blocks = 148 * 64;   // grid-stride beyond 64 blocks per SM
-    if (vec4 && marl) k_replay_store<4, 1><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);
+    const bool mask_ok = marl ? (src.mask_u8 == nullptr || (((uintptr_t)src.mask_u8) & 3) == 0)
+                              : (src.mask_f == nullptr || al16(src.mask_f));
+    if (vec4 && mask_ok && (long long)E * (m.A > m.N * m.N ? m.A : m.N * m.N) < (1ll << 31)) {
+        // flat float4 copies, one grid row per field (no per-element row arithmetic)
+        const long long slot0 = rb->mem_cntr % m.mem_size;
+        const int n_wrap = (int)((m.mem_size - slot0) < E ? (m.mem_size - slot0) : E);
+        const long long big = (long long)E * ((m.A > m.S ? m.A : m.S) / 4);
+        long long bx = (big + threads - 1) / threads;
+        if (bx > 148 * 8) bx = 148 * 8;
+        if (marl) k_replay_store_flat<1><<<dim3((unsigned)bx, 6), threads, 0, st>>>(m, slot0, n_wrap, E, src);
+        else k_replay_store_flat<0><<<dim3((unsigned)bx, 6), threads, 0, st>>>(m, slot0, n_wrap, E, src);
+    } else if (vec4 && marl) k_replay_store<4, 1><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);
     else if (vec4) k_replay_store<4, 0><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);
     else if (marl) k_replay_store<1, 1><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);
     else k_replay_store<1, 0><<<(int)blocks, threads, 0, st>>>(m, rb->mem_cntr, E, src);

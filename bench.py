@@ -464,6 +464,11 @@ def main():
     stats_sum.zero_()
     ranks.barrier()
     torch.cuda.synchronize()
+    if world > 1:
+        # the host-side barrier releases the ranks tens of microseconds apart; a tiny all-reduce on the stream
+        # makes the timed region START at the same device instant on every rank (its completion is
+        # simultaneous), so that max-over-ranks measures the slowest rank's work and not the barrier skew
+        dist.all_reduce(torch.zeros(1, device=dev))
     l0 = env.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -834,7 +834,11 @@ int chunk_steps(int T, size_t in_bytes_per_step) {
     if (tc < 1) tc = 1;
     int n = (T + tc - 1) / tc;
     if (n > kMaxChunks) n = kMaxChunks;
-    return (T + n - 1) / n;
+    int steps = (T + n - 1) / n;
+    // chunks start on 16-step boundaries: the stage tiling of the time-parallel kernels (k_sarl_mma_tma,
+    // k_marl_tma) is then the same as in one device launch over all T steps, and so is every result bit
+    if (steps > 16) steps = (steps + 15) / 16 * 16;
+    return steps;
 }
 
 }  // namespace

@@ -26,9 +26,10 @@ struct SarlBigOutMaps {
 
 constexpr int kBigThreads = 512;
 constexpr int kBigPartStride = 40;  // floats per (warp, g) row of the partial-sum area (32 used; pad breaks bank conflicts)
+constexpr int kBigPartFloats = 16 * 8 * kBigPartStride;  // one stage of partial sums (double buffered)
 __host__ __device__ constexpr int sarl_big_smem_bytes(int KQ, int V) {
     return 2 * (4 * KQ) * 2 * 32 * 16            // B fragments, two stages
-           + 16 * 8 * kBigPartStride * 4         // K-quarter partial sums
+           + 2 * kBigPartFloats * 4              // K-quarter partial sums, two stages
            + 4 * 4 * 8 * 16                      // max-plus composites [r][q][g]
            + 4 * 16 * 4                          // reward partial sums [r][step]
            + 6 * 16 * V * 4                      // out tile
@@ -55,8 +56,8 @@ __global__ void __launch_bounds__(kBigThreads, 1)
     unsigned char* base_g = big_smem_raw + (base_s - smem_u32(big_smem_raw));
     constexpr int BF_STAGE = KT * 2 * 32 * 16;
     uint4* const bf = reinterpret_cast<uint4*>(base_g);                                  // [2][KT][2][32]
-    float* const part = reinterpret_cast<float*>(base_g + 2 * BF_STAGE);                 // [16][8][kBigPartStride]
-    double2* const comps = reinterpret_cast<double2*>(part + 16 * 8 * kBigPartStride);   // [4][4][8]
+    float* const part = reinterpret_cast<float*>(base_g + 2 * BF_STAGE);                 // [2][16][8][kBigPartStride]
+    double2* const comps = reinterpret_cast<double2*>(part + 2 * kBigPartFloats);        // [4][4][8]
     float* const rsum = reinterpret_cast<float*>(comps + 4 * 4 * 8);                     // [4][16]
     float* const out_g = rsum + 4 * 16;                                                  // [6][16][V]
     const uint32_t out_s = base_s + (uint32_t)((unsigned char*)out_g - base_g);
@@ -142,28 +143,8 @@ __global__ void __launch_bounds__(kBigThreads, 1)
     float4* const part_w = reinterpret_cast<float4*>(part + (warp * 8 + g) * kBigPartStride + tig * 8);
     float* const out_w = out_g + sstep * V + ve;
 
-    load_phases(0);
-    load_scalars(0);
-    produce(0);
-    load_phases(1 < NS ? 1 : 0);
-    __syncthreads();
-
-    // values of step T - 1 (they become the env's state)
-    float f_rate = 0.f, f_dt = 0.f, f_dp = 0.f, f_overp = 0.f, f_overd = 0.f;
-    int f_arr = 0;
-    bool f_mine = false;
-
-    for (int k = 0; k < NS; ++k) {
-        // [A] theta of stage k + 1 -> the other fragment buffer; its phases were requested a stage ago
-        if (k + 1 < NS) {
-            produce(k + 1);
-            load_phases(k + 2 < NS ? k + 2 : k + 1);
-        }
-        const float a0 = na0, a1 = na1;
-        int arr = narr;
-        if (k + 1 < NS) load_scalars(k + 1);
-
-        // [B] my K-quarter of the stage's GEMM
+    // my K-quarter of stage k's GEMM: fragments bf[k & 1] -> partial sums part[k & 1]
+    auto mma_stage = [&](int k) {
         float mA[4] = {0.f, 0.f, 0.f, 0.f}, xA[4] = {0.f, 0.f, 0.f, 0.f};
         float mB[4] = {0.f, 0.f, 0.f, 0.f}, xB[4] = {0.f, 0.f, 0.f, 0.f};
         const uint4* bk = bf + ((k & 1) * KT * 2 + 2 * (KQ * q)) * 32 + lane;  // sets 2 j, 2 j + 1 of my k-tiles
@@ -177,20 +158,51 @@ __global__ void __launch_bounds__(kBigThreads, 1)
             mma_16816(xB, Ah[jj], fb.z, fb.w);
             mma_16816(xB, Al[jj], fb.x, fb.y);
         }
-        {  // partial S of my lane's four steps 4 tig + i: (Re, Im) pairs, i = 0, 1 from tile A, 2, 3 from tile B
-            part_w[0] = make_float4(mA[0] + xA[0], mA[2] + xA[2], mA[1] + xA[1], mA[3] + xA[3]);
-            part_w[1] = make_float4(mB[0] + xB[0], mB[2] + xB[2], mB[1] + xB[1], mB[3] + xB[3]);
-        }
-        if (is_t0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // out tile free again
-        __syncthreads();  // S1
+        // partial S of my lane's four steps 4 tig + i: (Re, Im) pairs, i = 0, 1 from tile A, 2, 3 from tile B
+        float4* pw = part_w + (k & 1) * (kBigPartFloats / 4);
+        pw[0] = make_float4(mA[0] + xA[0], mA[2] + xA[2], mA[1] + xA[1], mA[3] + xA[3]);
+        pw[1] = make_float4(mB[0] + xB[0], mB[2] + xB[2], mB[1] + xB[1], mB[3] + xB[3]);
+    };
 
-        // [C] per-step part (SARL:327-358) of my item: vehicle ve, step t = 16 k + sstep
+    // ---- software pipeline over the 16-step stages.  Between two block barriers every warp holds two
+    // INDEPENDENT instruction streams, so the float64 / shuffle chains of the per-step part overlap with
+    // sin/cos and tensor-core work of later stages:
+    //   segment 1:  produce theta fragments of stage k + 2   ||  per-step part of stage k, first half
+    //   segment 2:  GEMM of stage k + 1                      ||  per-step part of stage k, second half
+    load_phases(0);
+    load_scalars(0);
+    produce(0);
+    load_phases(1 < NS ? 1 : 0);
+    __syncthreads();
+    if (1 < NS) {
+        produce(1);
+        load_phases(2 < NS ? 2 : 1);
+    }
+    mma_stage(0);
+    __syncthreads();
+
+    // values of step T - 1 (they become the env's state)
+    float f_rate = 0.f, f_dt = 0.f, f_dp = 0.f, f_overp = 0.f, f_overd = 0.f;
+    int f_arr = 0;
+    bool f_mine = false;
+
+    for (int k = 0; k < NS; ++k) {
+        // ---- segment 1
+        if (k + 2 < NS) {  // theta of stage k + 2 -> the fragment buffer stage k used; its phases were requested earlier
+            produce(k + 2);
+            load_phases(k + 3 < NS ? k + 3 : k + 2);
+        }
+        const float a0 = na0, a1 = na1;
+        int arr = narr;
+        if (k + 1 < NS) load_scalars(k + 1);
+        // per-step part (SARL:327-358) of my item: vehicle ve, step t = 16 k + sstep
         const int t = k * R + sstep;
         const bool ok = eact && t < T;
         float re = 0.f, im = 0.f;
+        const float* pr = part_r + (k & 1) * kBigPartFloats;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
-            const float2 pq = *reinterpret_cast<const float2*>(part_r + qq * 8 * kBigPartStride);
+            const float2 pq = *reinterpret_cast<const float2*>(pr + qq * 8 * kBigPartStride);
             re += pq.x;
             im += pq.y;
         }
@@ -213,7 +225,10 @@ __global__ void __launch_bounds__(kBigThreads, 1)
         }
         const MaxPlus ex{__shfl_up_sync(kFull, f.a, 1, 4), __shfl_up_sync(kFull, f.b, 1, 4)};
         if (tig == 3) comps_r[q * 8] = make_double2(f.a, f.b);
+        if (is_t0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // out tile free again
         __syncthreads();  // S2
+        // ---- segment 2
+        if (k + 1 < NS) mma_stage(k + 1);
         MaxPlus before{0.0, -1.0e300}, whole{0.0, -1.0e300};  // identity maps (x -> max(x, -huge))
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(kBigThreads, 1)
         ru += __shfl_xor_sync(kFull, ru, 16);
         if (g == 0) rsum[r * 16 + sstep] = ru;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();  // S3: out tile, reward partial sums complete; fragment buffer k & 1 free
+        __syncthreads();  // S3: out tile, reward sums, partial sums of stage k + 1 and fragments of stage k + 2 complete
         if (is_t0) {
 #pragma unroll
             for (int n = 0; n < 6; ++n) tma_store_2d(&tm_out.trace[n], out_s + n * (TRACE_WORDS * 4), e * V, k * R);

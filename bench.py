@@ -228,9 +228,8 @@ def workload_config(args, world=1):
             "envs_per_gpu": args.envs, "V": args.V, "M": args.M, "T": args.T,
             "layout": "the reference's own array layout: action [T,E,2,V] f32, phase [T,E,M] f32, arrivals [T,E,V] i32 "
                       "in; one [T,E,V] f32 array per trace + reward [T,E] out (no packing / conversion pass anywhere)",
-            "stats_interval": "episode statistics are summed on device after every rollout (k_shard_stats) and "
-                              "all-reduced over the ranks ONCE per timed region (= statistics interval of "
-                              f"{args.steps} rollouts x {args.T} steps), inside the timed region",
+            "stats_interval": f"statistics interval = the timed region ({args.steps} rollouts x {args.T} steps); "
+                              "k_shard_stats runs after every rollout, inside the timed region",
             "l2_policy": "inputs+outputs of one launch exceed the 126 MB L2; nothing is re-read between launches"}
 
 
@@ -436,12 +435,38 @@ def main():
     wl = args.workload
     env, one_step, buf = make_rollout(torch, wl, E, V, M, T, local, rank, dev)
     stats_sum = torch.zeros(17, dtype=torch.float64, device=dev)
+    shared, stats_mode = None, "one device (no reduction)"
+    if world > 1:
+        # statistics reduction: rank 0's accumulator mapped into every rank (CUDA IPC over NVLink peer access);
+        # k_shard_stats adds each shard's sums into it with float64 atomics -- no collective, no rank waits.
+        # RISVEC_BENCH_STATS=nccl (or a failed mapping) selects ONE NCCL all-reduce per timed region instead.
+        ok = torch.ones(1, device=dev)
+        if os.environ.get("RISVEC_BENCH_STATS", "peer") == "peer":
+            try:
+                from ris_vec_marl_b200.dist import SharedStats
 
-    def episode_stats():  # per-rollout statistics stay on the device (one tiny kernel, no collective)
+                shared = SharedStats(local, rank, world)
+            except Exception as exc:  # all ranks must take the same path
+                sys.stderr.write(f"[bench] rank {rank}: peer mapping unavailable ({exc!r})\n")
+                ok.zero_()
+        else:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) < 1.0 and shared is not None:
+            shared.close()
+            shared = None
+        stats_mode = ("every rank sums its per-rollout statistics in its own HBM and, once per interval, adds the 17 sums "
+                      "into rank 0's accumulator with float64 atomics over NVLink peer memory (CUDA IPC mapping, one "
+                      "launch): no collective, no rank waits for another; totals read after the end barrier"
+                      if shared is not None else "one NCCL all-reduce of the 17-entry vector per timed region")
+
+    def episode_stats():  # per-rollout statistics: one tiny kernel, no collective
         env.shard_stats(out=stats_sum, accumulate=True)
 
-    def reduce_stats():   # the only collective on the path: once per statistics interval
-        if world > 1:
+    def reduce_stats():   # the only exchange on the path: once per statistics interval
+        if shared is not None:
+            shared.add_(stats_sum)
+        elif world > 1:
             dist.all_reduce(stats_sum)
 
     for _ in range(args.warmup):
@@ -462,6 +487,8 @@ def main():
                 break
         sampler.lines.clear()
     stats_sum.zero_()
+    if shared is not None:
+        shared.zero_()
     ranks.barrier()
     torch.cuda.synchronize()
     if world > 1:
@@ -469,6 +496,10 @@ def main():
         # makes the timed region START at the same device instant on every rank (its completion is
         # simultaneous), so that max-over-ranks measures the slowest rank's work and not the barrier skew
         dist.all_reduce(torch.zeros(1, device=dev))
+        # ... followed by a ~0.25 ms device-side spin: the rank whose host joined that all-reduce last would
+        # otherwise start its timed region with an EMPTY queue (its first rollout is still being enqueued by
+        # python) and time its own launch latency; every rank's queue is full when the spin ends
+        torch.cuda._sleep(500_000)
     l0 = env.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -485,7 +516,9 @@ def main():
     ev[2].record()
     torch.cuda.synchronize()
     ranks.barrier()
-    launches = env.launch_count - l0
+    launches = env.launch_count - l0 + (1 if shared is not None else 0)   # + the interval's k_atomic_add_f64
+    stats_total = shared.read() if shared is not None else stats_sum.cpu()
+    mean_reward = float(stats_total[16]) / (world * E * args.steps)
     ms_local = ev[0].elapsed_time(ev[2])
     kern_ms = sorted(a.elapsed_time(b) for a, b in kev)
     kern_ms_avg = sum(kern_ms) / len(kern_ms)
@@ -558,8 +591,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clocks,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args, world), stats_reduction=stats_mode),
+            "clocks": clocks, "mean_reward_last_steps": mean_reward,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps,
                     "per_rank": [{"rank": r, "ms_per_step": s * 1e3, "h2d_gbs": h2d / s / 1e9, "d2h_gbs": d2h / s / 1e9}
@@ -568,7 +602,7 @@ def main():
                                "memory / root-complex bandwidth (per-rank GB/s above), the kernel is <1 % of the step",
                     "lean": e2e_lean},
             "gpu_launches": launches,
-            "ranks": [{"rank": r, "ms_total": v[0], "kernel_ms_avg": v[1], "stats_allreduce_drain_ms": v[2],
+            "ranks": [{"rank": r, "ms_total": v[0], "kernel_ms_avg": v[1], "stats_reduce_ms": v[2],
                        "host_enqueue_us_per_step": v[3]} for r, v in enumerate(per_rank)],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),

@@ -359,6 +359,20 @@ int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* 
  * to out [RISVEC_NSTAT + 1] f64 (device). */
 int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream);
 
+/* Statistics reduction WITHOUT a collective (one node, NVLink / NVSwitch): one rank creates a small device buffer
+ * and publishes its 64-byte CUDA IPC handle; every other rank (= process) maps it and passes the mapped pointer as
+ * `out` of risvec_shard_stats(accumulate != 0).  k_shard_stats then adds the shard's sums into the owner's HBM with
+ * float64 atomics over peer memory (or sums locally and pushes once per interval with risvec_shared_buffer_add):
+ * no rank waits for another, nothing but 17 atomics per block / interval crosses NVLink;
+ * the owner reads the totals after the job's own barrier.  (The portable alternative is an all-reduce of the
+ * vector: ris_vec_marl_b200/dist.py.)  owner != 0 frees the buffer, owner == 0 unmaps it. */
+int risvec_shared_buffer_create(int device, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]);
+int risvec_shared_buffer_open(int device, const unsigned char ipc_handle[64], void** dev_ptr);
+int risvec_shared_buffer_close(int device, void* dev_ptr, int owner);
+/* dst[i] += src[i] (float64 atomics, i < n) on `stream`: a rank that sums its statistics locally over an interval
+ * pushes them into the (peer-mapped) accumulator with ONE launch per interval. */
+int risvec_shared_buffer_add(int device, double* dst, const double* src, int n, void* stream);
+
 /* Host-side call counters that key the on-device Philox draws of make_new_game, renew_positions and the channel /
  * Random_phase draws (out / in = {reset, mobility, channel}).  Together with the RISVEC_F_* fields (which
  * include step_ctr, the key of the arrival draws) and the params they are the whole state of a handle:

@@ -1368,6 +1368,53 @@ int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* str
     return check_launch(env, "k_shard_stats");
 }
 
+// ---- a device buffer other processes of the job can map (CUDA IPC over NVLink peer access)
+int risvec_shared_buffer_create(int device, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]) {
+    if (!dev_ptr || !ipc_handle || bytes == 0) return fail(RISVEC_ERR_INVALID, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    ENTER_DEVICE(device);
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    CUDA_TRY(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(RISVEC_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle, &h, 64);
+    *dev_ptr = p;
+    return RISVEC_OK;
+}
+int risvec_shared_buffer_open(int device, const unsigned char ipc_handle[64], void** dev_ptr) {
+    if (!dev_ptr || !ipc_handle) return fail(RISVEC_ERR_INVALID, "bad arguments");
+    ENTER_DEVICE(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+    return RISVEC_OK;
+}
+__global__ void k_atomic_add_f64(double* __restrict__ dst, const double* __restrict__ src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(dst + i, src[i]);    // dst may be peer memory: a red.global.add.f64 over NVLink
+}
+int risvec_shared_buffer_add(int device, double* dst, const double* src, int n, void* stream) {
+    if (!dst || !src || n <= 0) return fail(RISVEC_ERR_INVALID, "bad arguments");
+    ENTER_DEVICE(device);
+    k_atomic_add_f64<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dst, src, n);
+    CUDA_TRY(cudaGetLastError());
+    return RISVEC_OK;
+}
+int risvec_shared_buffer_close(int device, void* dev_ptr, int owner) {
+    if (!dev_ptr) return RISVEC_OK;
+    ENTER_DEVICE(device);
+    if (owner) CUDA_TRY(cudaFree(dev_ptr));
+    else CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return RISVEC_OK;
+}
+
 int risvec_get_rng_counters(const risvec_env_t* env, uint64_t out[3]) {
     if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
     out[0] = env->reset_calls; out[1] = env->mob_calls; out[2] = env->chan_calls;

@@ -12,6 +12,7 @@
 #include "step.cuh"
 #include "sarl_mma.cuh"
 #include "sarl_mma_big.cuh"
+#include "sarl_umma.cuh"
 #include "marl_tma.cuh"
 #include "pairing.cuh"
 #include "replay.cuh"
@@ -88,6 +89,7 @@ struct risvec_env {
     cudaStream_t s_in, s_out;
     cudaEvent_t ev[2 * 64 + 2];  // 2 * kMaxChunks + 2
     int force_generic;  // RISVEC_FORCE_GENERIC=1: always use the shape-generic kernels (tests)
+    int sarl_umma;      // large shapes: k_sarl_umma (tcgen05) unless RISVEC_SARL_PATH=mma-sync (k_sarl_mma_big)
     int sarl_path;      // RISVEC_SARL_PATH = auto (0) | mma (1) | v8 (2) | generic (3): tests / A-B runs
     int sarl_tma;       // RISVEC_SARL_TMA = 0 keeps the mma path on its LDG kernel (tests / A-B runs)
     int marl_tma;       // RISVEC_MARL_PATH = v8 keeps the MARL fast path on k_marl_v8 (tests / A-B runs)
@@ -325,6 +327,27 @@ int launch_sarl_mma_big(risvec_env* env, const SarlArgs& a, cudaStream_t st, boo
     *launched = true;
     return check_step_launch(env, "k_sarl_mma_big");
 }
+// tcgen05 form of the same rollout (sarl_umma.cuh): the default for these shapes; RISVEC_SARL_PATH=mma-sync keeps
+// the mma.sync kernel above for A/B runs
+template <int KQ>
+int launch_sarl_umma(risvec_env* env, const SarlArgs& a, cudaStream_t st, bool* launched) {
+    *launched = false;
+    const int E = env->dims.E, V = env->dims.V, T = a.T;
+    SarlBigOutMaps tm;
+    const risvec_sarl_out_t& o = a.out;
+    float* const traces[6] = {o.DataBuf, o.data_t, o.data_p, o.over_power, o.over_data, o.rate};
+    for (int n = 0; n < 6; ++n)
+        if (!tensor_map_2d(&tm.trace[n], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, traces[n], (uint64_t)E * V, T, V, 16))
+            return RISVEC_OK;  // not encodable: the caller falls back
+    static const uint32_t lbo = [] { const char* v = getenv("RISVEC_UMMA_LBO"); return v ? (uint32_t)atoi(v) : 128u; }();
+    static const uint32_t sbo = [] { const char* v = getenv("RISVEC_UMMA_SBO"); return v ? (uint32_t)atoi(v) : 256u; }();
+    auto kern = k_sarl_umma<KQ>;
+    const int smem = sarl_umma_smem_bytes(KQ, V);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<E, kUmmaThreads, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm, lbo, sbo);
+    *launched = true;
+    return check_step_launch(env, "k_sarl_umma");
+}
 inline bool sarl_big_covers(const risvec_env* env, const SarlArgs& a) {
     const risvec_sarl_out_t& o = a.out;
     const int V = env->dims.V, M = env->dims.M;
@@ -356,9 +379,14 @@ int launch_sarl(risvec_env* env, const SarlArgs& a, cudaStream_t st) {
     }
     if ((path == kAuto || path == kMma) && a.in_rec == nullptr && sarl_big_covers(env, a) && env->sarl_tma) {
         bool launched = false;
-        const int rc = M <= 64 ? launch_sarl_mma_big<2>(env, a, st, &launched)
-                               : (M <= 128 ? launch_sarl_mma_big<4>(env, a, st, &launched)
-                                           : launch_sarl_mma_big<8>(env, a, st, &launched));
+        int rc;
+        if (env->sarl_umma)
+            rc = M <= 64 ? launch_sarl_umma<2>(env, a, st, &launched)
+                         : (M <= 128 ? launch_sarl_umma<4>(env, a, st, &launched) : launch_sarl_umma<8>(env, a, st, &launched));
+        else
+            rc = M <= 64 ? launch_sarl_mma_big<2>(env, a, st, &launched)
+                         : (M <= 128 ? launch_sarl_mma_big<4>(env, a, st, &launched)
+                                     : launch_sarl_mma_big<8>(env, a, st, &launched));
         if (rc != RISVEC_OK || launched) return rc;
     }
     if (VP <= 8 && M <= 40 && path != kGeneric)  // elements split over the env's 8 lanes (FP32 pipe)
@@ -488,6 +516,11 @@ int risvec_create(const risvec_params_t* params, int variant, int E, int V, int 
         if (sp && !strcmp(sp, "mma-ldg")) {  // the tensor-core path without the TMA staging
             env->sarl_path = 1;
             env->sarl_tma = 0;
+        }
+        env->sarl_umma = 1;
+        if (sp && !strcmp(sp, "mma-sync")) {  // large shapes: the mma.sync kernel instead of the tcgen05 one
+            env->sarl_path = 1;
+            env->sarl_umma = 0;
         }
     }
     Dims& d = env->dims;

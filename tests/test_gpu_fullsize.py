@@ -39,7 +39,8 @@ SARL_PATHS = [("mma", 8, 40, 4096, "k_sarl_mma_tma"), ("mma-ldg", 8, 40, 4096, "
               ("mma", 8, 16, 4096, "k_sarl_mma_tma"), ("mma", 8, 24, 4096, "k_sarl_mma"), ("v8", 8, 40, 4096, "k_sarl_v8"),
               ("packed", 8, 40, 4096, "k_sarl_v8"), ("generic", 8, 40, 4096, "k_sarl_rollout"),
               ("generic", 8, 64, 4096, "k_sarl_cascade2+k_sarl_scan"),
-              ("mma", 32, 256, 1024, "k_sarl_mma_big"),                      # BASELINE config 4
+              ("mma", 32, 256, 1024, "k_sarl_umma"),                         # BASELINE config 4 (tcgen05)
+              ("mma-sync", 32, 256, 1024, "k_sarl_mma_big"), ("mma", 16, 128, 1024, "k_sarl_umma"),
               ("generic", 32, 256, 1024, "k_sarl_cascade2+k_sarl_scan")]
 
 

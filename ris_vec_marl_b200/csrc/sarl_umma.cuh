@@ -80,6 +80,7 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&r)[8]
 }
 
 template <int KQ>
+// (17 warps are allotted registers as 20: at most 96 per thread)
 __global__ void __launch_bounds__(kUmmaThreads, 1)
     k_sarl_umma(Dims d, State s, const SarlConsts c, SarlArgs a, const __grid_constant__ SarlBigOutMaps tm_out,
                 const uint32_t lbo, const uint32_t sbo) {
@@ -137,10 +138,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
             if (!(vact && m < M)) wa = make_double2(0.0, 0.0);
             if (!(vact && m + 1 < M)) wb = make_double2(0.0, 0.0);
             uint2 reh, rel, imh, iml;
-            split_h2(wa.x, -wa.y, reh.x, rel.x);  // row Re S_v: ( Re w, -Im w) at K = 2 m, 2 m + 1
-            split_h2(wb.x, -wb.y, reh.y, rel.y);
-            split_h2(wa.y, wa.x, imh.x, iml.x);   // row Im S_v: ( Im w,  Re w)
-            split_h2(wb.y, wb.x, imh.y, iml.y);
+            // (one float64 -> float32 conversion per value, then the float32 split: the two pieces carry 22 bits)
+            const float ax = (float)wa.x, ay = (float)wa.y, bx = (float)wb.x, by = (float)wb.y;
+            split_h2(ax, -ay, reh.x, rel.x);  // row Re S_v: ( Re w, -Im w) at K = 2 m, 2 m + 1
+            split_h2(bx, -by, reh.y, rel.y);
+            split_h2(ay, ax, imh.x, iml.x);   // row Im S_v: ( Im w,  Re w)
+            split_h2(by, bx, imh.y, iml.y);
             const int koff = (p >> 2) * 4096 + ((p & 3) >> 1) * 128 + (p & 1) * 8;
             const int o_re = koff + (row_re >> 3) * 256 + (row_re & 7) * 16, o_im = koff + (row_im >> 3) * 256 + (row_im & 7) * 16;
             *reinterpret_cast<uint2*>(base_g + o_re) = reh;
@@ -180,34 +183,34 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         const double* const h_other = hbuf + (wq * 2 + (set ^ 1)) * 8;
         const uint32_t bar_h_mine = bar_h + 8 * (wq * 2 + set), bar_h_other = bar_h + 8 * (wq * 2 + (set ^ 1));
         const int bar_id = 1 + set;
-        float na0[4], na1[4];
-        int narr[4] = {0, 0, 0, 0};
+        struct Scalars {  // action rows and arrivals of my four steps (by value: they must stay in registers)
+            float4 a0, a1;
+            int4 arr;
+        };
         auto load_scalars = [&](int k) {
+            unsigned t[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const unsigned t = (unsigned)min(k * R + 4 * tig + i, T - 1);
-                na0[i] = __ldg(ac_w + t * s2V);
-                na1[i] = __ldg(ac_w + t * s2V + V);
-                if (ar_w != nullptr) narr[i] = __ldg(ar_w + t * sVv);
-            }
+            for (int i = 0; i < 4; ++i) t[i] = (unsigned)min(k * R + 4 * tig + i, T - 1);
+            Scalars r;
+            r.a0 = make_float4(__ldg(ac_w + t[0] * s2V), __ldg(ac_w + t[1] * s2V), __ldg(ac_w + t[2] * s2V), __ldg(ac_w + t[3] * s2V));
+            r.a1 = make_float4(__ldg(ac_w + t[0] * s2V + V), __ldg(ac_w + t[1] * s2V + V), __ldg(ac_w + t[2] * s2V + V),
+                               __ldg(ac_w + t[3] * s2V + V));
+            r.arr = make_int4(0, 0, 0, 0);
+            if (ar_w != nullptr)
+                r.arr = make_int4(__ldg(ar_w + t[0] * sVv), __ldg(ar_w + t[1] * sVv), __ldg(ar_w + t[2] * sVv), __ldg(ar_w + t[3] * sVv));
+            return r;
         };
         float f_rate = 0.f, f_dt = 0.f, f_dp = 0.f, f_overp = 0.f, f_overd = 0.f;
         int f_arr = 0;
         bool f_mine = false;
         double buf = s.databuf[ev];  // DataBuf before stage 0 (set 0 starts from the state)
-        if (set < NS) load_scalars(set);
+        Scalars nxt = load_scalars(min(set, NS - 1));
         for (int k = set; k < NS; k += 2) {
             const int n = k >> 1;
-            float2 a0[2], a1[2];
-            int arr[4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                a0[h] = make_float2(na0[2 * h], na0[2 * h + 1]);
-                a1[h] = make_float2(na1[2 * h], na1[2 * h + 1]);
-                arr[2 * h] = narr[2 * h];
-                arr[2 * h + 1] = narr[2 * h + 1];
-            }
-            if (k + 2 < NS) load_scalars(k + 2);
+            const float2 a0[2] = {make_float2(nxt.a0.x, nxt.a0.y), make_float2(nxt.a0.z, nxt.a0.w)};
+            const float2 a1[2] = {make_float2(nxt.a1.x, nxt.a1.y), make_float2(nxt.a1.z, nxt.a1.w)};
+            int arr[4] = {nxt.arr.x, nxt.arr.y, nxt.arr.z, nxt.arr.w};
+            if (k + 2 < NS) nxt = load_scalars(k + 2);
             // ---- the accumulators of stage k: rows g (Re) and g + 8 (Im) of my lane quarter, my four steps
             mbar_wait(bar_dfull + 8 * set, (uint32_t)n & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -342,7 +342,7 @@ int launch_sarl_umma(risvec_env* env, const SarlArgs& a, cudaStream_t st, bool* 
     static const uint32_t lbo = [] { const char* v = getenv("RISVEC_UMMA_LBO"); return v ? (uint32_t)atoi(v) : 128u; }();
     static const uint32_t sbo = [] { const char* v = getenv("RISVEC_UMMA_SBO"); return v ? (uint32_t)atoi(v) : 256u; }();
     auto kern = k_sarl_umma<KQ>;
-    const int smem = sarl_umma_smem_bytes(KQ, V);
+    const int smem = sarl_umma_smem_request(KQ, V);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<E, kUmmaThreads, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm, lbo, sbo);
     *launched = true;

@@ -1,22 +1,23 @@
 // SARL rollout for MANY vehicles / RIS elements (BASELINE config 4: V = 32, M = 256) on the 5th-generation
 // tensor cores: the cascaded reduction of one env, the real GEMM  [2V x 2M] . [2M x T]  (SARL:149-171), is
-// issued as tcgen05.mma (M = 128, N = 32, K = 16) by ONE thread, operands in shared memory, the accumulators
-// in tensor memory.  One thread block per env.  Reference: Simulation-SARL/Environment.py:125-131, 149-171,
+// issued as tcgen05.mma (M = 128, N = 32, K = 16) by ONE thread: the constant operand A and the accumulators
+// live in tensor memory, the per-stage operand B in shared memory.  One thread block per env.  Reference: Simulation-SARL/Environment.py:125-131, 149-171,
 // 318-359.  Same operand split as sarl_mma.cuh (x = hi + lo in binary16, float32 accumulation, the hi*hi
 // product in its own accumulator) and the same max-plus treatment of the DataBuf recursion.  Both pieces of
 // both operands ride in ONE instruction per k-step: the rows of A are (hi rows | lo rows), the columns of B
 // (hi steps | lo steps), so D holds the four partial products side by side and the step warps add them.
 //
-//   A  [128 x 16 KT] binary16, K-major core matrices (8 rows x 16 bytes), no swizzle: the geometry phasors
-//      w(v, m) = z_v^m of the env, written ONCE per rollout (4 KB per k-step).  Tensor-memory lane quarter q
-//      (rows 32 q .. 32 q + 31) belongs to vehicles 8 q .. 8 q + 7: rows 32 q + g / + 8 + g = hi piece of the
-//      Re S / Im S row of vehicle 8 q + g, rows 32 q + 16 + g / + 24 + g = the lo piece of the same rows.
-//   B  [32 x 16 KT] binary16, same layout, double buffered: theta = exp(j*phase) of a 16-step stage, rows
+//   A  [128 x 16 KT] binary16 in TENSOR MEMORY (lane = row, one 32-bit column per RIS element = its two K
+//      values; 8 KT columns): the geometry phasors w(v, m) = z_v^m of the env, written ONCE per rollout with
+//      tcgen05.st by the 16 non-MMA warps.  Lane quarter q (rows 32 q .. 32 q + 31) belongs to vehicles
+//      8 q .. 8 q + 7: rows 32 q + g / + 8 + g = hi piece of the Re S / Im S row of vehicle 8 q + g, rows
+//      32 q + 16 + g / + 24 + g = the lo piece of the same rows.
+//   B  [32 x 16 KT] binary16 in shared memory, K-major core matrices (8 rows x 16 bytes), no swizzle, double buffered: theta = exp(j*phase) of a 16-step stage, rows
 //      0-15 the hi piece, rows 16-31 the lo piece, produced by 8 warps (packed sin/cos polynomial, split, one
 //      8-byte store per piece and element pair).  Tile row c (mod 16) holds step 4 ((c & 7) >> 1) + 2 (c >> 3)
 //      + (c & 1) of the stage, so that the accumulator fragment of a lane (tcgen05.ld 16x256b) is FOUR
 //      CONSECUTIVE steps of one vehicle.
-//   D  [128 x 32] float32 per stage, double buffered (64 tensor-memory columns in all): columns 0-15 = . x hi
+//   D  [128 x 32] float32 per stage, double buffered (64 tensor-memory columns after A): columns 0-15 = . x hi
 //      theta, 16-31 = . x lo theta.
 //
 // Warp roles (they only meet at mbarriers):
@@ -27,9 +28,9 @@
 //                    before, so the only serial link is a hand-off of 8 doubles per warp (hbuf + mbarrier).
 //   warps 8-15       producers of B (stage k + 1 while stage k multiplies)
 //   warp 16          one lane: waits "B full" + "D empty", issues KT tcgen05.mma, commits to "B empty" + "D full"
-// (A first version issued three M = 64, N = 16 instructions per k-step into two accumulators: 96 per stage at
-//  ~60 cycles each were the whole stage time -- the shared-memory operand fetch of so small an instruction is
-//  not hidden.)
+// (History: A in shared memory cost one 4 KB operand fetch per instruction -- the tensor core pulled ~40 B per
+//  clock from these unswizzled tiles, 32 x 5 KB = the whole 2.2 us stage; three M = 64, N = 16 instructions per
+//  k-step before that were slower still.  With A in tensor memory an instruction fetches 1 KB of B.)
 #pragma once
 #include "sarl_mma.cuh"
 #include "sarl_mma_big.cuh"
@@ -38,19 +39,25 @@ namespace risvec {
 
 constexpr int kUmmaStepWarps = 8, kUmmaProdWarps = 8;
 constexpr int kUmmaThreads = 32 * (kUmmaStepWarps + kUmmaProdWarps + 1);
-constexpr int kUmmaTmemCols = 64;
+__host__ __device__ constexpr int umma_tmem_cols(int KQ) {  // A (8 KT columns) + 2 x 32 accumulator columns, power of two
+    return 32 * KQ + 64 <= 128 ? 128 : (32 * KQ + 64 <= 256 ? 256 : 512);
+}
 // instruction descriptor of tcgen05.mma kind::f16: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28
 constexpr uint32_t kUmmaIdesc = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 __host__ __device__ constexpr int sarl_umma_smem_bytes(int KQ, int V) {
-    return (4 * KQ) * 4096               // A (hi and lo rows)
-           + 2 * (4 * KQ) * 1024         // B [buffer] (hi and lo rows)
+    return 2 * (4 * KQ) * 1024           // B [buffer] (hi and lo rows)
            + 2 * 6 * 16 * V * 4          // out tiles of the two step-warp sets
            + 2 * 4 * 16 * 4              // reward partial sums [set][warp][step]
            + 4 * 2 * 8 * 8               // DataBuf hand-off [warp][writer set][vehicle]
            + 16 * 8 + 16                 // mbarriers, tensor-memory base address
            + 256;                        // alignment slack
+}
+// one block per SM (a block owns up to all 512 tensor-memory columns): the launch asks for more than half of the
+// SM's shared memory whatever the block needs
+__host__ __device__ constexpr int sarl_umma_smem_request(int KQ, int V) {
+    return sarl_umma_smem_bytes(KQ, V) > 120 * 1024 ? sarl_umma_smem_bytes(KQ, V) : 120 * 1024;
 }
 
 // shared-memory matrix descriptor: K-major, no swizzle; core matrices of one 8-row group are 128 B apart
@@ -66,6 +73,18 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uin
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -85,10 +104,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
     k_sarl_umma(Dims d, State s, const SarlConsts c, SarlArgs a, const __grid_constant__ SarlBigOutMaps tm_out,
                 const uint32_t lbo, const uint32_t sbo) {
     constexpr int KT = 4 * KQ, R = 16;
-    constexpr int A_BYTES = KT * 4096, B_BYTES = KT * 1024;
+    constexpr int B_BYTES = KT * 1024, A_COLS = 8 * KT, TMEM_COLS = umma_tmem_cols(KQ);
     extern __shared__ unsigned char umma_smem_raw[];
     const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
-    const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    int lane_id = threadIdx.x & 31;
+    asm volatile("" : "+r"(lane_id));  // opaque: keeps ptxas from re-deriving lane-dependent addresses from %tid in the loops
+    const int lane = lane_id, g = lane >> 2, tig = lane & 3;
     const int E = d.E, V = d.V, M = d.M, T = a.T;
     const int e = blockIdx.x;
     const int NS = (T + R - 1) / R;
@@ -97,12 +118,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
     // ---- shared memory carve-up (128 B aligned)
     const uint32_t base_s = (smem_u32(umma_smem_raw) + 127u) & ~127u;
     unsigned char* const base_g = umma_smem_raw + (base_s - smem_u32(umma_smem_raw));
-    const uint32_t a_s = base_s;
-    const uint32_t b_s = base_s + A_BYTES;                             // + buffer * B_BYTES
-    unsigned char* const b_g = base_g + A_BYTES;
+    const uint32_t b_s = base_s;                                       // + buffer * B_BYTES
     const int TRACE_WORDS = R * V;
     const uint32_t out_s = b_s + 2 * B_BYTES;                          // + set * 6 TRACE_WORDS 4
-    float* const out_g = reinterpret_cast<float*>(base_g + A_BYTES + 2 * B_BYTES);
+    float* const out_g = reinterpret_cast<float*>(base_g + 2 * B_BYTES);
     float* const rsum = out_g + 2 * 6 * TRACE_WORDS;                   // [set][4][16]
     double* const hbuf = reinterpret_cast<double*>(rsum + 2 * 4 * 16);  // [warp][writer set][8]
     const uint32_t bars = out_s + 2 * 6 * TRACE_WORDS * 4 + 2 * 4 * 16 * 4 + 4 * 2 * 8 * 8;
@@ -120,44 +139,46 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         for (int i = 0; i < 8; ++i) mbar_init(bar_h + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kUmmaStepWarps + kUmmaProdWarps) {  // tensor memory: 64 columns (two stages x two accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kUmmaTmemCols) : "memory");
+    if (warp == kUmmaStepWarps + kUmmaProdWarps) {  // tensor memory: A + two stages of accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
-        // ---- A operand, once per rollout: thread -> vehicle v, element pairs p0 + 16 i (elements 2 p, 2 p + 1)
-        const int v = (lane & 7) + 8 * (warp & 3), p0 = (lane >> 3) + 4 * (warp >> 2);
-        const bool vact = v < V;
-        const double2 z = unit_phasor64(d.angle_BR - s.angle[(size_t)e * V + min(v, V - 1)]);  // w(v, m) = z^m (SARL:134-145)
-        const double2 z2 = cmul64(z, z), z4 = cmul64(z2, z2), z8 = cmul64(z4, z4), z16 = cmul64(z8, z8), z32 = cmul64(z16, z16);
-        double2 w = cpow64(z, 2u * (unsigned)p0);
-        const int row_re = 32 * (v >> 3) + (v & 7), row_im = row_re + 8;  // hi piece; the lo piece sits 16 rows further
-#pragma unroll
-        for (int i = 0; i < KT / 4; ++i) {
-            const int p = p0 + 16 * i, m = 2 * p;
-            double2 wa = w, wb = cmul64(w, z);
-            if (!(vact && m < M)) wa = make_double2(0.0, 0.0);
-            if (!(vact && m + 1 < M)) wb = make_double2(0.0, 0.0);
-            uint2 reh, rel, imh, iml;
-            // (one float64 -> float32 conversion per value, then the float32 split: the two pieces carry 22 bits)
-            const float ax = (float)wa.x, ay = (float)wa.y, bx = (float)wb.x, by = (float)wb.y;
-            split_h2(ax, -ay, reh.x, rel.x);  // row Re S_v: ( Re w, -Im w) at K = 2 m, 2 m + 1
-            split_h2(bx, -by, reh.y, rel.y);
-            split_h2(ay, ax, imh.x, iml.x);   // row Im S_v: ( Im w,  Re w)
-            split_h2(by, bx, imh.y, iml.y);
-            const int koff = (p >> 2) * 4096 + ((p & 3) >> 1) * 128 + (p & 1) * 8;
-            const int o_re = koff + (row_re >> 3) * 256 + (row_re & 7) * 16, o_im = koff + (row_im >> 3) * 256 + (row_im & 7) * 16;
-            *reinterpret_cast<uint2*>(base_g + o_re) = reh;
-            *reinterpret_cast<uint2*>(base_g + o_re + 2 * 256) = rel;
-            *reinterpret_cast<uint2*>(base_g + o_im) = imh;
-            *reinterpret_cast<uint2*>(base_g + o_im + 2 * 256) = iml;
-            w = cmul64(w, z32);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tensor core reads A through the async proxy
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_d = tmem + A_COLS;  // accumulators: + 32 * buffer
+    if (warp < kUmmaStepWarps + kUmmaProdWarps) {
+        // ---- A operand, once per rollout: warp -> lane quarter q = warp & 3 and the elements [2 KT kp, 2 KT (kp + 1)),
+        // kp = warp >> 2; lane i -> row 32 q + i: vehicle 8 q + (i & 7), Re / Im row (bit 3), hi / lo piece (bit 4)
+        const int q = warp & 3, kp = warp >> 2;
+        const int v = 8 * q + (lane & 7);
+        const bool im_row = (lane >> 3) & 1, lo_piece = (lane >> 4) & 1;
+        const bool vact = v < V;
+        const double2 z = unit_phasor64(d.angle_BR - s.angle[(size_t)e * V + min(v, V - 1)]);  // w(v, m) = z^m (SARL:134-145)
+        double2 w = cpow64(z, (unsigned)(2 * KT * kp));
+        const uint32_t t_a = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(2 * KT * kp);
+#pragma unroll 1
+        for (int cch = 0; cch < KT / 4; ++cch) {  // 8 elements = 8 columns per store
+            uint32_t col[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = 2 * KT * kp + 8 * cch + i;
+                const bool on = vact && m < M;
+                // K = 2 m, 2 m + 1: row Re S_v holds (Re w, -Im w), row Im S_v holds (Im w, Re w)
+                const float x0 = on ? (float)(im_row ? w.y : w.x) : 0.f, x1 = on ? (float)(im_row ? w.x : -w.y) : 0.f;
+                uint32_t hi, lo;
+                split_h2(x0, x1, hi, lo);
+                col[i] = lo_piece ? lo : hi;
+                w = cmul64(w, z);
+            }
+            tmem_st_32x32b_x8(t_a + 8 * cch, col);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (warp < kUmmaStepWarps) {
         // ================================ step warps ================================
@@ -173,7 +194,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         const float* const ac_w = a.action + (unsigned)e * 2 * V + vc;
         const int* const ar_w = a.arrivals != nullptr ? a.arrivals + (unsigned)e * V + vc : nullptr;
         // my lane quarter: lanes 0-15 the hi rows, 16-31 the lo rows; columns 0-15 x hi theta, 16-31 x lo theta
-        const uint32_t t_hh = tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)(32 * set), t_hl = t_hh + 16;
+        const uint32_t t_hh = tmem_d + ((uint32_t)(32 * wq) << 16) + (uint32_t)(32 * set), t_hl = t_hh + 16;
         const uint32_t t_lh = t_hh + (16u << 16), t_ll = t_lh + 16;
         float* const tile = out_g + set * 6 * TRACE_WORDS;
         const uint32_t tile_s = out_s + (uint32_t)set * 6 * TRACE_WORDS * 4;
@@ -373,15 +394,38 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         const int pw = warp - kUmmaStepWarps, rh = pw & 1, j0 = pw >> 1;
         constexpr int NT = KT / 4;
         const int row_step = 4 * (g >> 1) + 2 * rh + (g & 1);
-        const unsigned sM = (unsigned)E * M;
-        const float* const ph_w = a.phase + (unsigned)e * M + 8 * j0 + 2 * tig;     // + t sM + 32 u
-        unsigned char* const b_w = b_g + j0 * 1024 + rh * 256 + (tig >> 1) * 128 + g * 16 + (tig & 1) * 8;  // + buffer B_BYTES + piece 512 + u 4096
+        const size_t sM = (size_t)E * M;
+        const bool full = M == 8 * KT;  // every element block of every lane exists (block-uniform fast path)
+        const int nu = min(NT, max(0, (M - 8 * j0 - 2 * tig + 31) >> 5));  // my element blocks j0 + 4 u that hold elements
+        const float* const ph_w = a.phase + (size_t)e * M + 8 * j0 + 2 * tig;
+        const float* q_last = ph_w + (size_t)(T - 1) * sM;
+        const float* q = ph_w + (size_t)row_step * sM;  // my row of the stage to load next (clamped to step T - 1)
+        size_t q_stride = (size_t)R * sM;
+        asm volatile("" : "+l"(q_last), "+l"(q), "+l"(q_stride));  // opaque: held in registers, not re-derived per load
+        // my 8 bytes of every element block: + buffer B_BYTES + piece 512 + u 4096
+        const uint32_t b_w = b_s + (uint32_t)(j0 * 1024 + rh * 256 + (tig >> 1) * 128 + g * 16 + (tig & 1) * 8);
         float2 ph[NT];
         auto load_phases = [&](int k) {
-            const float* q0 = ph_w + (unsigned)min(k * R + row_step, T - 1) * sM;
+            const float* qq = (k * R + row_step < T) ? q : q_last;
+            q += q_stride;
+            asm volatile("" : "+l"(qq));  // one address register pair for the loads below
+            if (full) {
 #pragma unroll
-            for (int u = 0; u < NT; ++u)
-                ph[u] = (8 * (j0 + 4 * u) + 2 * tig < M) ? __ldg(reinterpret_cast<const float2*>(q0 + 32 * u)) : make_float2(0.f, 0.f);
+                for (int u = 0; u < NT; ++u) ph[u] = __ldg(reinterpret_cast<const float2*>(qq + 32 * u));
+            } else {
+#pragma unroll
+                for (int u = 0; u < NT; ++u)
+                    ph[u] = u < nu ? __ldg(reinterpret_cast<const float2*>(qq + 32 * u)) : make_float2(0.f, 0.f);
+            }
+        };
+        auto make_block = [&](float2 phase2, uint32_t dst) {
+            float2 sn, cs;
+            sincos_pi2(phase2, &sn, &cs);  // theta = exp(j*phase) (SARL:125-131)
+            uint2 hi, lo;
+            split_h2(cs.x, sn.x, hi.x, lo.x);  // element 8 j + 2 tig:     K = (cos, sin)
+            split_h2(cs.y, sn.y, hi.y, lo.y);  // element 8 j + 2 tig + 1
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(hi.x), "r"(hi.y) : "memory");
+            asm volatile("st.shared.v2.b32 [%0+512], {%1, %2};" ::"r"(dst), "r"(lo.x), "r"(lo.y) : "memory");
         };
         load_phases(0);
         for (int k = 0; k < NS; ++k) {
@@ -391,18 +435,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
             for (int u = 0; u < NT; ++u) cur[u] = ph[u];
             if (k + 1 < NS) load_phases(k + 1);
             mbar_wait(bar_bempty + 8 * b, (((uint32_t)k >> 1) & 1u) ^ 1u);  // the MMAs of stage k - 2 have read this buffer
-            unsigned char* dst = b_w + b * B_BYTES;
+            const uint32_t dst = b_w + (uint32_t)b * B_BYTES;
+            if (full) {
 #pragma unroll
-            for (int u = 0; u < NT; ++u) {
-                if (j0 + 4 * u < kt_run) {
-                    float2 sn, cs;
-                    sincos_pi2(cur[u], &sn, &cs);  // theta = exp(j*phase) (SARL:125-131)
-                    uint2 hi, lo;
-                    split_h2(cs.x, sn.x, hi.x, lo.x);  // element 8 j + 2 tig:     K = (cos, sin)
-                    split_h2(cs.y, sn.y, hi.y, lo.y);  // element 8 j + 2 tig + 1
-                    *reinterpret_cast<uint2*>(dst + u * 4096) = hi;
-                    *reinterpret_cast<uint2*>(dst + 512 + u * 4096) = lo;
-                }
+                for (int u = 0; u < NT; ++u) make_block(cur[u], dst + u * 4096);
+            } else {
+#pragma unroll
+                for (int u = 0; u < NT; ++u)
+                    if (j0 + 4 * u < kt_run) make_block(cur[u], dst + u * 4096);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -417,12 +457,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
                 mbar_wait(bar_bfull + 8 * b, par);
                 mbar_wait(bar_dempty + 8 * b, par ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_acc = tmem + (uint32_t)(32 * b);
-                uint64_t ad = umma_desc(a_s, lbo, sbo), bd = umma_desc(b_s + b * B_BYTES, lbo, sbo);
+                const uint32_t d_acc = tmem_d + (uint32_t)(32 * b);
+                uint64_t bd = umma_desc(b_s + b * B_BYTES, lbo, sbo);
                 for (int j = 0; j < kt_run; ++j) {
-                    umma_f16_ss(d_acc, ad, bd, kUmmaIdesc, j > 0);
-                    ad += 4096 >> 4;  // next k-step: the start address field counts 16-byte units
-                    bd += 1024 >> 4;
+                    umma_f16_ts(d_acc, tmem + 8 * j, bd, kUmmaIdesc, j > 0);  // A: 8 columns (16 K values) per k-step
+                    bd += 1024 >> 4;  // B: next k-step; the start address field counts 16-byte units
                 }
                 umma_commit(bar_bempty + 8 * b);  // B buffer reusable once these MMAs have read it
                 umma_commit(bar_dfull + 8 * b);   // ... and the accumulators complete
@@ -436,7 +475,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == kUmmaStepWarps + kUmmaProdWarps)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kUmmaTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
 }  // namespace risvec

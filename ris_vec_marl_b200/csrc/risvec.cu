@@ -339,12 +339,18 @@ int launch_sarl_umma(risvec_env* env, const SarlArgs& a, cudaStream_t st, bool* 
     for (int n = 0; n < 6; ++n)
         if (!tensor_map_2d(&tm.trace[n], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, traces[n], (uint64_t)E * V, T, V, 16))
             return RISVEC_OK;  // not encodable: the caller falls back
+    CUtensorMap tm_ac, tm_ar;  // a stage's action rows [16][2 V] and arrivals [16][V] of the block's env
+    if (!tensor_map_2d(&tm_ac, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.action, (uint64_t)E * 2 * V, T, 2 * V, 16)) return RISVEC_OK;
+    if (a.arrivals == nullptr)
+        tm_ar = tm_ac;  // unused: arrivals are drawn on the device
+    else if (!tensor_map_2d(&tm_ar, CU_TENSOR_MAP_DATA_TYPE_INT32, a.arrivals, (uint64_t)E * V, T, V, 16))
+        return RISVEC_OK;
     static const uint32_t lbo = [] { const char* v = getenv("RISVEC_UMMA_LBO"); return v ? (uint32_t)atoi(v) : 128u; }();
     static const uint32_t sbo = [] { const char* v = getenv("RISVEC_UMMA_SBO"); return v ? (uint32_t)atoi(v) : 256u; }();
     auto kern = k_sarl_umma<KQ>;
     const int smem = sarl_umma_smem_request(KQ, V);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<E, kUmmaThreads, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm, lbo, sbo);
+    kern<<<E, kUmmaThreads, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm, tm_ac, tm_ar, lbo, sbo);
     *launched = true;
     return check_step_launch(env, "k_sarl_umma");
 }

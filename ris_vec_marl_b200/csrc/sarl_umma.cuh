@@ -49,9 +49,10 @@ constexpr uint32_t kUmmaIdesc = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) <<
 __host__ __device__ constexpr int sarl_umma_smem_bytes(int KQ, int V) {
     return 2 * (4 * KQ) * 1024           // B [buffer] (hi and lo rows)
            + 2 * 6 * 16 * V * 4          // out tiles of the two step-warp sets
+           + 2 * 2 * 16 * 3 * V * 4      // input tiles [set][buffer]: actions [16][2 V] + arrivals [16][V] (TMA)
            + 2 * 4 * 16 * 4              // reward partial sums [set][warp][step]
            + 4 * 2 * 8 * 8               // DataBuf hand-off [warp][writer set][vehicle]
-           + 16 * 8 + 16                 // mbarriers, tensor-memory base address
+           + 20 * 8 + 16                 // mbarriers, tensor-memory base address
            + 256;                        // alignment slack
 }
 // one block per SM (a block owns up to all 512 tensor-memory columns): the launch asks for more than half of the
@@ -102,7 +103,8 @@ template <int KQ>
 // (17 warps are allotted registers as 20: at most 96 per thread)
 __global__ void __launch_bounds__(kUmmaThreads, 1)
     k_sarl_umma(Dims d, State s, const SarlConsts c, SarlArgs a, const __grid_constant__ SarlBigOutMaps tm_out,
-                const uint32_t lbo, const uint32_t sbo) {
+                const __grid_constant__ CUtensorMap tm_ac, const __grid_constant__ CUtensorMap tm_ar, const uint32_t lbo,
+                const uint32_t sbo) {
     constexpr int KT = 4 * KQ, R = 16;
     constexpr int B_BYTES = KT * 1024, A_COLS = 8 * KT, TMEM_COLS = umma_tmem_cols(KQ);
     extern __shared__ unsigned char umma_smem_raw[];
@@ -122,13 +124,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
     const int TRACE_WORDS = R * V;
     const uint32_t out_s = b_s + 2 * B_BYTES;                          // + set * 6 TRACE_WORDS 4
     float* const out_g = reinterpret_cast<float*>(base_g + 2 * B_BYTES);
-    float* const rsum = out_g + 2 * 6 * TRACE_WORDS;                   // [set][4][16]
+    const int IN_BYTES = R * 3 * V * 4;                                // one input tile: actions [16][2 V] | arrivals [16][V]
+    const uint32_t in_s = out_s + 2 * 6 * TRACE_WORDS * 4;             // + (set * 2 + buffer) * IN_BYTES
+    unsigned char* const in_g = reinterpret_cast<unsigned char*>(out_g + 2 * 6 * TRACE_WORDS);
+    float* const rsum = reinterpret_cast<float*>(in_g + 4 * IN_BYTES);  // [set][4][16]
     double* const hbuf = reinterpret_cast<double*>(rsum + 2 * 4 * 16);  // [warp][writer set][8]
-    const uint32_t bars = out_s + 2 * 6 * TRACE_WORDS * 4 + 2 * 4 * 16 * 4 + 4 * 2 * 8 * 8;
+    const uint32_t bars = in_s + 4 * IN_BYTES + 2 * 4 * 16 * 4 + 4 * 2 * 8 * 8;
     // mbarriers: B full [2] (8 producer warps), B empty [2] (commit), D full [2] (commit), D empty [2] (4 step warps),
-    //            hand-off [4 warps][2 writer sets] (1)
+    //            hand-off [4 warps][2 writer sets] (1), inputs full [2 sets][2 buffers] (TMA transaction bytes)
     const uint32_t bar_bfull = bars, bar_bempty = bars + 16, bar_dfull = bars + 32, bar_dempty = bars + 48, bar_h = bars + 64;
-    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(base_g + (bars + 128 - base_s));
+    const uint32_t bar_in = bars + 128;
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(base_g + (bars + 160 - base_s));
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_bfull + 8 * i, kUmmaProdWarps);
@@ -137,7 +143,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
             mbar_init(bar_dempty + 8 * i, 4);
         }
         for (int i = 0; i < 8; ++i) mbar_init(bar_h + 8 * i, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bar_in + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == kUmmaStepWarps + kUmmaProdWarps) {  // tensor memory: A + two stages of accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -155,22 +163,37 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         const int v = 8 * q + (lane & 7);
         const bool im_row = (lane >> 3) & 1, lo_piece = (lane >> 4) & 1;
         const bool vact = v < V;
+        // The four lanes of a vehicle (Re / Im row x hi / lo piece) share the float64 work: lane c = lane >> 3 walks
+        // the elements m = c (mod 4) of the warp's range (w <- w z^4), rounds them to float32 and the four exchange
+        // them by shuffles; every lane then splits the value ITS row holds.
+        const int c4 = lane >> 3;
         const double2 z = unit_phasor64(d.angle_BR - s.angle[(size_t)e * V + min(v, V - 1)]);  // w(v, m) = z^m (SARL:134-145)
-        double2 w = cpow64(z, (unsigned)(2 * KT * kp));
+        const double2 z2 = cmul64(z, z), z4 = cmul64(z2, z2);
+        double2 w = cpow64(z, (unsigned)(2 * KT * kp + c4));
         const uint32_t t_a = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(2 * KT * kp);
+        { // L2 prefetch of the first two stages' phase rows (the producers' first loads then come from L2)
+            const int t = threadIdx.x;  // 512 threads: 32 rows x 16 segments of 64 B ... of up to 1 KB per row
+            const int row = min(t >> 4, T - 1), seg = (t & 15) * 16;
+            if (seg < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.phase + ((size_t)row * E + e) * M + seg));
+        }
 #pragma unroll 1
         for (int cch = 0; cch < KT / 4; ++cch) {  // 8 elements = 8 columns per store
             uint32_t col[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = 2 * KT * kp + 8 * cch + i;
-                const bool on = vact && m < M;
-                // K = 2 m, 2 m + 1: row Re S_v holds (Re w, -Im w), row Im S_v holds (Im w, Re w)
-                const float x0 = on ? (float)(im_row ? w.y : w.x) : 0.f, x1 = on ? (float)(im_row ? w.x : -w.y) : 0.f;
-                uint32_t hi, lo;
-                split_h2(x0, x1, hi, lo);
-                col[i] = lo_piece ? lo : hi;
-                w = cmul64(w, z);
+            for (int h = 0; h < 2; ++h) {
+                const float wx = (float)w.x, wy = (float)w.y;  // element 2 KT kp + 8 cch + 4 h + c4
+                w = cmul64(w, z4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int m = 2 * KT * kp + 8 * cch + 4 * h + i;
+                    const float ex = __shfl_sync(kFull, wx, (lane & 7) + 8 * i), ey = __shfl_sync(kFull, wy, (lane & 7) + 8 * i);
+                    const bool on = vact && m < M;
+                    // K = 2 m, 2 m + 1: row Re S_v holds (Re w, -Im w), row Im S_v holds (Im w, Re w)
+                    const float x0 = on ? (im_row ? ey : ex) : 0.f, x1 = on ? (im_row ? ex : -ey) : 0.f;
+                    uint32_t hi, lo;
+                    split_h2(x0, x1, hi, lo);
+                    col[4 * h + i] = lo_piece ? lo : hi;
+                }
             }
             tmem_st_32x32b_x8(t_a + 8 * cch, col);
         }
@@ -190,9 +213,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         const bool leader = wq == 0 && lane == 0;
         const float coef = vact ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
         const long long step0 = s.step_ctr[e];
-        const unsigned s2V = (unsigned)E * 2 * V, sVv = (unsigned)E * V;
-        const float* const ac_w = a.action + (unsigned)e * 2 * V + vc;
-        const int* const ar_w = a.arrivals != nullptr ? a.arrivals + (unsigned)e * V + vc : nullptr;
         // my lane quarter: lanes 0-15 the hi rows, 16-31 the lo rows; columns 0-15 x hi theta, 16-31 x lo theta
         const uint32_t t_hh = tmem_d + ((uint32_t)(32 * wq) << 16) + (uint32_t)(32 * set), t_hl = t_hh + 16;
         const uint32_t t_lh = t_hh + (16u << 16), t_ll = t_lh + 16;
@@ -204,34 +224,42 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         const double* const h_other = hbuf + (wq * 2 + (set ^ 1)) * 8;
         const uint32_t bar_h_mine = bar_h + 8 * (wq * 2 + set), bar_h_other = bar_h + 8 * (wq * 2 + (set ^ 1));
         const int bar_id = 1 + set;
-        struct Scalars {  // action rows and arrivals of my four steps (by value: they must stay in registers)
-            float4 a0, a1;
-            int4 arr;
+        // action rows and arrivals of a stage arrive by TMA in the set's input tiles (two in flight per set); the
+        // leader issues the tile of stage k + 4 once the set has read the one of stage k
+        const bool has_ar = a.arrivals != nullptr;
+        auto issue_inputs = [&](int kk) {  // leader only
+            const int nb = (kk >> 1) & 1;
+            const uint32_t dst = in_s + (uint32_t)(set * 2 + nb) * IN_BYTES, bar = bar_in + 8 * (set * 2 + nb);
+            mbar_expect_tx(bar, (uint32_t)(R * 2 * V * 4 + (has_ar ? R * V * 4 : 0)));
+            tma_load_2d(dst, &tm_ac, e * 2 * V, kk * R, bar);
+            if (has_ar) tma_load_2d(dst + R * 2 * V * 4, &tm_ar, e * V, kk * R, bar);
         };
-        auto load_scalars = [&](int k) {
-            unsigned t[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) t[i] = (unsigned)min(k * R + 4 * tig + i, T - 1);
-            Scalars r;
-            r.a0 = make_float4(__ldg(ac_w + t[0] * s2V), __ldg(ac_w + t[1] * s2V), __ldg(ac_w + t[2] * s2V), __ldg(ac_w + t[3] * s2V));
-            r.a1 = make_float4(__ldg(ac_w + t[0] * s2V + V), __ldg(ac_w + t[1] * s2V + V), __ldg(ac_w + t[2] * s2V + V),
-                               __ldg(ac_w + t[3] * s2V + V));
-            r.arr = make_int4(0, 0, 0, 0);
-            if (ar_w != nullptr)
-                r.arr = make_int4(__ldg(ar_w + t[0] * sVv), __ldg(ar_w + t[1] * sVv), __ldg(ar_w + t[2] * sVv), __ldg(ar_w + t[3] * sVv));
-            return r;
-        };
+        if (leader) {
+            if (set < NS) issue_inputs(set);
+            if (set + 2 < NS) issue_inputs(set + 2);
+        }
         float f_rate = 0.f, f_dt = 0.f, f_dp = 0.f, f_overp = 0.f, f_overd = 0.f;
         int f_arr = 0;
         bool f_mine = false;
         double buf = s.databuf[ev];  // DataBuf before stage 0 (set 0 starts from the state)
-        Scalars nxt = load_scalars(min(set, NS - 1));
         for (int k = set; k < NS; k += 2) {
             const int n = k >> 1;
-            const float2 a0[2] = {make_float2(nxt.a0.x, nxt.a0.y), make_float2(nxt.a0.z, nxt.a0.w)};
-            const float2 a1[2] = {make_float2(nxt.a1.x, nxt.a1.y), make_float2(nxt.a1.z, nxt.a1.w)};
-            int arr[4] = {nxt.arr.x, nxt.arr.y, nxt.arr.z, nxt.arr.w};
-            if (k + 2 < NS) nxt = load_scalars(k + 2);
+            float2 a0[2], a1[2];
+            int arr[4] = {0, 0, 0, 0};
+            {
+                mbar_wait(bar_in + 8 * (set * 2 + (n & 1)), (uint32_t)(n >> 1) & 1u);
+                const float* ac = reinterpret_cast<const float*>(in_g + (set * 2 + (n & 1)) * IN_BYTES) + (4 * tig) * 2 * V + vc;
+                const int* ar = reinterpret_cast<const int*>(in_g + (set * 2 + (n & 1)) * IN_BYTES + R * 2 * V * 4) + (4 * tig) * V + vc;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    a0[h] = make_float2(ac[(2 * h) * 2 * V], ac[(2 * h + 1) * 2 * V]);
+                    a1[h] = make_float2(ac[(2 * h) * 2 * V + V], ac[(2 * h + 1) * 2 * V + V]);
+                    if (has_ar) {
+                        arr[2 * h] = ar[(2 * h) * V];
+                        arr[2 * h + 1] = ar[(2 * h + 1) * V];
+                    }
+                }
+            }
             // ---- the accumulators of stage k: rows g (Re) and g + 8 (Im) of my lane quarter, my four steps
             mbar_wait(bar_dfull + 8 * set, (uint32_t)n & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -319,6 +347,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
             // ---- my set's out tile is free again once the TMA stores of its previous stage have read it
             if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             named_bar_sync(bar_id, 128);
+            if (leader && k + 4 < NS) {  // every warp of the set has read the stage's input tile: refill it
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_inputs(k + 4);
+            }
             float rew[4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {

@@ -17,8 +17,8 @@
 //      8-byte store per piece and element pair).  Tile row c (mod 16) holds step 4 ((c & 7) >> 1) + 2 (c >> 3)
 //      + (c & 1) of the stage, so that the accumulator fragment of a lane (tcgen05.ld 16x256b) is FOUR
 //      CONSECUTIVE steps of one vehicle.
-//   D  [128 x 32] float32 per stage, double buffered (64 tensor-memory columns after A): columns 0-15 = . x hi
-//      theta, 16-31 = . x lo theta.
+//   D  [128 x 32] float32, columns 0-15 = . x hi theta, 16-31 = . x lo theta; kUmmaChains accumulators per stage
+//      (k-step j adds into chain j % kUmmaChains), double buffered, in the tensor-memory columns after A.
 //
 // Warp roles (they only meet at mbarriers):
 //   warps 0-3 / 4-7  step warps of the even / odd stages: warp q reads rows 32 q .. 32 q + 31 of D (its
@@ -28,9 +28,13 @@
 //                    before, so the only serial link is a hand-off of 8 doubles per warp (hbuf + mbarrier).
 //   warps 8-15       producers of B (stage k + 1 while stage k multiplies)
 //   warp 16          one lane: waits "B full" + "D empty", issues KT tcgen05.mma, commits to "B empty" + "D full"
-// (History: A in shared memory cost one 4 KB operand fetch per instruction -- the tensor core pulled ~40 B per
-//  clock from these unswizzled tiles, 32 x 5 KB = the whole 2.2 us stage; three M = 64, N = 16 instructions per
-//  k-step before that were slower still.  With A in tensor memory an instruction fetches 1 KB of B.)
+// Measured (B200, globaltimer stamps per block, T = 256): tensor-memory allocation 0.26 us, A 4.0 us, first B
+// stage 1.7 us later, then one stage per 1.5 us, 1.7 us from the last "D full" to the end of the block: 33 us per
+// env.  The steady state is bound by the tensor core's DISPATCH of these small instructions: 32 per stage take
+// 1.44 us (~83 clocks each, where the datapath needs 16) -- the same with N = 64 per instruction (timing
+// experiment) and the same with two alternating accumulator chains, so it is neither operand bandwidth nor the
+// accumulate dependency.  (History: with A in shared memory an instruction took ~128 clocks, three M = 64,
+// N = 16 instructions per k-step ~62 clocks each.)
 #pragma once
 #include "sarl_mma.cuh"
 #include "sarl_mma_big.cuh"
@@ -39,9 +43,17 @@ namespace risvec {
 
 constexpr int kUmmaStepWarps = 8, kUmmaProdWarps = 8;
 constexpr int kUmmaThreads = 32 * (kUmmaStepWarps + kUmmaProdWarps + 1);
-__host__ __device__ constexpr int umma_tmem_cols(int KQ) {  // A (8 KT columns) + 2 x 32 accumulator columns, power of two
-    return 32 * KQ + 64 <= 128 ? 128 : (32 * KQ + 64 <= 256 ? 256 : 512);
+#ifndef RISVEC_UMMA_CHAINS
+#define RISVEC_UMMA_CHAINS 2
+#endif
+// accumulators per stage: k-step j adds into chain j % kUmmaChains and the step warps add the chains.  Not for
+// speed (the instruction rate does not depend on it) but for accuracy: the tensor core adds every k-step into a
+// float32 D of magnitude ~sqrt(2 M); shorter chains keep that rounding inside the rate tolerance at M = 256.
+constexpr int kUmmaChains = RISVEC_UMMA_CHAINS;
+__host__ __device__ constexpr int umma_tmem_cols(int KQ) {  // A (8 KT columns) + 2 stages x chains x 32 columns, power of two
+    return 32 * KQ + 64 * kUmmaChains <= 128 ? 128 : (32 * KQ + 64 * kUmmaChains <= 256 ? 256 : 512);
 }
+static_assert(32 * 8 + 64 * kUmmaChains <= 512, "tensor memory: A of the largest shape + the accumulators");
 // instruction descriptor of tcgen05.mma kind::f16: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28
 constexpr uint32_t kUmmaIdesc = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
@@ -155,7 +167,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_d = tmem + A_COLS;  // accumulators: + 32 * buffer
+    constexpr int D_COLS = 32 * kUmmaChains;  // one stage of accumulators
+    const uint32_t tmem_d = tmem + A_COLS;    // + D_COLS * buffer + 32 * chain
+    const int n_chains = min(kUmmaChains, kt_run);
     if (warp < kUmmaStepWarps + kUmmaProdWarps) {
         // ---- A operand, once per rollout: warp -> lane quarter q = warp & 3 and the elements [2 KT kp, 2 KT (kp + 1)),
         // kp = warp >> 2; lane i -> row 32 q + i: vehicle 8 q + (i & 7), Re / Im row (bit 3), hi / lo piece (bit 4)
@@ -163,9 +177,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         const int v = 8 * q + (lane & 7);
         const bool im_row = (lane >> 3) & 1, lo_piece = (lane >> 4) & 1;
         const bool vact = v < V;
-        // The four lanes of a vehicle (Re / Im row x hi / lo piece) share the float64 work: lane c = lane >> 3 walks
-        // the elements m = c (mod 4) of the warp's range (w <- w z^4), rounds them to float32 and the four exchange
-        // them by shuffles; every lane then splits the value ITS row holds.
+        // The four lanes of a vehicle (Re / Im row x hi / lo piece) share the work: lane c = lane >> 3 walks the
+        // elements m = c (mod 4) of the warp's range (w <- w z^4, float64), rounds to float32 and splits ONCE:
+        // P = (hi Re w, hi Im w), Q = (lo Re w, lo Im w) as packed binary16 pairs.  Every row of the vehicle is a
+        // permutation of those: the Re S row holds (Re w, -Im w) = the pair with the sign of its high half
+        // flipped, the Im S row (Im w, Re w) = the pair with its halves swapped (rounding is symmetric).
         const int c4 = lane >> 3;
         const double2 z = unit_phasor64(d.angle_BR - s.angle[(size_t)e * V + min(v, V - 1)]);  // w(v, m) = z^m (SARL:134-145)
         const double2 z2 = cmul64(z, z), z4 = cmul64(z2, z2);
@@ -181,18 +197,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
             uint32_t col[8];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const float wx = (float)w.x, wy = (float)w.y;  // element 2 KT kp + 8 cch + 4 h + c4
+                const bool on = vact && 2 * KT * kp + 8 * cch + 4 * h + c4 < M;  // my element of this group of four
+                uint32_t P, Q;
+                split_h2(on ? (float)w.x : 0.f, on ? (float)w.y : 0.f, P, Q);
                 w = cmul64(w, z4);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int m = 2 * KT * kp + 8 * cch + 4 * h + i;
-                    const float ex = __shfl_sync(kFull, wx, (lane & 7) + 8 * i), ey = __shfl_sync(kFull, wy, (lane & 7) + 8 * i);
-                    const bool on = vact && m < M;
-                    // K = 2 m, 2 m + 1: row Re S_v holds (Re w, -Im w), row Im S_v holds (Im w, Re w)
-                    const float x0 = on ? (im_row ? ey : ex) : 0.f, x1 = on ? (im_row ? ex : -ey) : 0.f;
-                    uint32_t hi, lo;
-                    split_h2(x0, x1, hi, lo);
-                    col[4 * h + i] = lo_piece ? lo : hi;
+                    const uint32_t p = __shfl_sync(kFull, P, (lane & 7) + 8 * i), qq = __shfl_sync(kFull, Q, (lane & 7) + 8 * i);
+                    const uint32_t x = lo_piece ? qq : p;
+                    col[4 * h + i] = im_row ? __byte_perm(x, x, 0x1032) : (x ^ 0x80000000u);
                 }
             }
             tmem_st_32x32b_x8(t_a + 8 * cch, col);
@@ -214,7 +227,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
         const float coef = vact ? (float)(s.amp[ev] / (kSigma * kSigma)) : 0.f;  // SARL:157-159
         const long long step0 = s.step_ctr[e];
         // my lane quarter: lanes 0-15 the hi rows, 16-31 the lo rows; columns 0-15 x hi theta, 16-31 x lo theta
-        const uint32_t t_hh = tmem_d + ((uint32_t)(32 * wq) << 16) + (uint32_t)(32 * set), t_hl = t_hh + 16;
+        const uint32_t t_hh = tmem_d + ((uint32_t)(32 * wq) << 16) + (uint32_t)(D_COLS * set), t_hl = t_hh + 16;
         const uint32_t t_lh = t_hh + (16u << 16), t_ll = t_lh + 16;
         float* const tile = out_g + set * 6 * TRACE_WORDS;
         const uint32_t tile_s = out_s + (uint32_t)set * 6 * TRACE_WORDS * 4;
@@ -273,6 +286,22 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dx[i] = (hl[i] + lh[i]) + ll[i];
+#pragma unroll
+                for (int ch = 1; ch < kUmmaChains; ++ch) {
+                    if (ch < n_chains) {  // block-uniform
+                        float hh[8];
+                        tmem_ld_16x256b_x2(t_hh + 32 * ch, hh);
+                        tmem_ld_16x256b_x2(t_hl + 32 * ch, hl);
+                        tmem_ld_16x256b_x2(t_lh + 32 * ch, lh);
+                        tmem_ld_16x256b_x2(t_ll + 32 * ch, ll);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            dm[i] += hh[i];
+                            dx[i] += (hl[i] + lh[i]) + ll[i];
+                        }
+                    }
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -489,10 +518,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
                 mbar_wait(bar_bfull + 8 * b, par);
                 mbar_wait(bar_dempty + 8 * b, par ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_acc = tmem_d + (uint32_t)(32 * b);
+                const uint32_t d_acc = tmem_d + (uint32_t)(D_COLS * b);
                 uint64_t bd = umma_desc(b_s + b * B_BYTES, lbo, sbo);
                 for (int j = 0; j < kt_run; ++j) {
-                    umma_f16_ts(d_acc, tmem + 8 * j, bd, kUmmaIdesc, j > 0);  // A: 8 columns (16 K values) per k-step
+                    // A: 8 columns (16 K values) per k-step; D: chain j % kUmmaChains
+                    umma_f16_ts(d_acc + 32 * (j % kUmmaChains), tmem + 8 * j, bd, kUmmaIdesc, j >= kUmmaChains);
                     bd += 1024 >> 4;  // B: next k-step; the start address field counts 16-byte units
                 }
                 umma_commit(bar_bempty + 8 * b);  // B buffer reusable once these MMAs have read it

@@ -74,19 +74,24 @@ def test_sarl_4096_envs_rollout_matches_oracle(path, V, M, E, kernel):
     assert np.array_equal(env.pos_x.cpu().numpy(), o.pos[..., 0]) and np.array_equal(env.pos_y.cpu().numpy(), o.pos[..., 1])
     ra = sarl_rate_atol(M)
     n_band = 0
+    worst = 0.0
     for t in range(T):
         rew, over_p = o.step_sarl(acts[t], phs[t])
         band = sarl_reward_band(o.last["buf_signed"], o.over_data, M).any(axis=1)  # reward penalties jump here
         n_band += int(band.sum())
-        close(got["rate"][t], o.vehicle_rate, ra, f"rate t={t}")
+        worst = max(worst, float((np.abs(got["rate"][t] - o.vehicle_rate) / (ra + RTOL * np.abs(o.vehicle_rate))).max()))
         close(got["data_p"][t], o.data_p, 1e-5, f"data_p t={t}")
         close(got["DataBuf"][t], o.DataBuf, 4 * ra, f"DataBuf t={t}")
         close(got["over_data"][t], o.over_data, 4 * ra, f"over_data t={t}")
-        close(got["over_power"][t], over_p, 4e-6, f"over_power t={t}")
+        # over_power = P1 - localProcRev(DataBuf + data_p): |d over_power / d DataBuf| <= 3 c_rev^3 x^2 <= 0.7 (x <= 4.31 kbit),
+        # so the rate's absolute floor (sqrt(M) growth, tests/parity.py) reaches it scaled by 0.7
+        close(got["over_power"][t], over_p, 4e-6 + 0.7 * ra, f"over_power t={t}")
         close(got["reward"][t], rew, 4e-6, f"reward t={t}", mask=band)
+    assert worst <= 1.0, f"rate: worst error {worst:.2f} of its tolerance ({ra:.2e} + {RTOL:g} |rate|)"
     # the reward is the RL signal: it must be compared on (nearly) every env-step
     assert n_band <= 0.05 * E * T, f"{n_band} of {E * T} env-steps band-excluded from the reward check"
-    print(f"[{kernel}] reward compared on {E * T - n_band} of {E * T} env-steps ({n_band} on a penalty threshold)")
+    print(f"[{kernel}] reward compared on {E * T - n_band} of {E * T} env-steps ({n_band} on a penalty threshold); "
+          f"worst rate error = {worst:.2f} of its tolerance")
     # the state after the rollout is the last step's
     np.testing.assert_allclose(env.DataBuf.cpu().numpy(), o.DataBuf, rtol=RTOL, atol=4 * ra)
     close(env.reward.cpu().numpy(), rew, 4e-6, "state reward", mask=band)

@@ -372,6 +372,11 @@ def secondary_block(torch, ranks, args, rank, local, dev, peak):
         flops = 8.0 * V4 * M4 * E4 * T4
         c4["sarl_step"]["cascade_tflops"] = flops / (c4["sarl_step"]["ms_per_launch"] * 1e-3) / 1e12
         del env, one, buf
+        for key, path in (("sarl_step_mma_sync_kernel", "mma-sync"), ("sarl_step_round1_kernels", "generic")):  # A/B arms
+            env, one, buf = make_rollout(torch, "sarl", E4, V4, M4, T4, local, rank, dev, sarl_path=path)
+            c4[key] = kernel_line(torch, ranks, "sarl", E4, V4, M4, T4, one, env, peak, n=5)
+            del env, one, buf
+        c4["sarl_speedup_vs_round1_kernels"] = c4["sarl_step_round1_kernels"]["ms_per_launch"] / c4["sarl_step"]["ms_per_launch"]
         env, one, buf = make_rollout(torch, "marl", E4, V4, M4, T4, local, rank, dev)
         c4["marl_step"] = kernel_line(torch, ranks, "marl", E4, V4, M4, T4, one, env, peak, n=5)
         c4["bcd_us_per_launch"] = ranks.max(event_time_launches(torch, env.optimize_phase_shift, 5)[0]) * 1e3

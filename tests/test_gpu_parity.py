@@ -421,3 +421,28 @@ def test_masked_reset_touches_only_the_selected_envs():
         env.rollout_marl(torch.rand(5, E, 2, V, device="cuda"), torch.full((E, V), -1, dtype=torch.int32, device="cuda"),
                          torch.full((E,), V, dtype=torch.int32, device="cuda"),
                          out={"rate": torch.empty(4, E, V, device="cuda")})
+
+
+def test_shared_statistics_accumulator_single_process():
+    """`dist.SharedStats` (risvec_shared_buffer_*): the owner's side of the peer-memory statistics reduction.
+    (The mapping by a second process and the equality with an NCCL all-reduce: tools/check_shared_stats.py
+    under torchrun.)"""
+    from ris_vec_marl_b200 import BatchedEnviron
+    from ris_vec_marl_b200._lib import NSTAT
+    from ris_vec_marl_b200.dist import SharedStats
+
+    E, V, M = 256, 8, 40
+    env = BatchedEnviron("sarl", E, V, M, seed=5)
+    env.make_new_game(); env.renew_positions(); env.compute_parms()
+    shared = SharedStats(0, 0, 1)
+    shared.zero_()
+    local = torch.zeros(NSTAT + 1, dtype=torch.float64, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(3):
+        env.step_sarl(torch.rand(E, 2, V, device="cuda", generator=g), torch.rand(E, M, device="cuda", generator=g) * 6.28)
+        env.shard_stats(out=local, accumulate=True)              # per-rollout sums stay local ...
+        env.shard_stats(out=shared.tensor, accumulate=True)      # ... or go straight into the accumulator
+    shared.add_(local)                                           # the per-interval push
+    total = shared.read()
+    assert torch.equal(total, 2.0 * local.cpu()) and float(total[NSTAT]) != 0.0
+    shared.close()

@@ -580,6 +580,44 @@ def main():
                     "h2d_bytes_per_step": (h_act.numel() + h_ph.numel()) * 4,
                     "d2h_bytes_per_step": sum(v.numel() * 4 for v in lean.values()), "kernel": env.last_kernel(),
                     "what": "arrivals drawn on the device (Philox), 5 of the 7 traces copied back"}
+    # the copy roofline of the e2e step, measured here: this rank's host<->device link with plain pinned copies of
+    # the step's byte counts, one direction alone and both directions at once (two streams)
+    pcie = None
+    try:
+        hb_in = torch.empty(h2d, dtype=torch.uint8).pin_memory()
+        hb_out = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+        db_in = torch.empty(h2d, dtype=torch.uint8, device=dev)
+        db_out = torch.empty(d2h, dtype=torch.uint8, device=dev)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copy_ms(do_in, do_out, reps=3):
+            torch.cuda.synchronize()
+            ranks.barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            s_in.wait_event(a0); s_out.wait_event(a0)
+            for _ in range(reps):
+                if do_in:
+                    with torch.cuda.stream(s_in):
+                        db_in.copy_(hb_in, non_blocking=True)
+                if do_out:
+                    with torch.cuda.stream(s_out):
+                        hb_out.copy_(db_out, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s_in); torch.cuda.current_stream().wait_stream(s_out)
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / reps
+
+        copy_ms(True, True, 1)
+        t_in, t_out, t_both = copy_ms(True, False), copy_ms(False, True), copy_ms(True, True)
+        pcie = {"h2d_alone_gbs": h2d / t_in / 1e6, "d2h_alone_gbs": d2h / t_out / 1e6,
+                "both_directions_ms_per_step": ranks.max(t_both),
+                "copy_bound_value": world * E * T / (ranks.max(t_both) * 1e-3),
+                "what": "plain pinned cudaMemcpyAsync of one step's H2D and D2H byte counts on two streams, all ranks at "
+                        "once: the env-steps/s a zero-cost kernel would reach through this host link"}
+        del hb_in, hb_out, db_in, db_out
+    except Exception as exc:  # a measurement aid, never fatal
+        pcie = {"error": repr(exc)[:200]}
     del h_act, h_arr, h_o
     peak, peak_src = measured_peak_gbs()
     secondary = None
@@ -603,6 +641,7 @@ def main():
                     "steps": args.e2e_steps,
                     "per_rank": [{"rank": r, "ms_per_step": s * 1e3, "h2d_gbs": h2d / s / 1e9, "d2h_gbs": d2h / s / 1e9}
                                  for r, s in enumerate(step_s)],
+                    "copy_roofline": pcie,
                     "limiter": "host<->device copies: PCIe Gen5 x16 per GPU at N=1; at N>1 the ranks share the host's "
                                "memory / root-complex bandwidth (per-rank GB/s above), the kernel is <1 % of the step",
                     "lean": e2e_lean},

@@ -259,6 +259,15 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
 int risvec_observe(risvec_env_t* env, float* obs, void* stream);
 int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float* phase, void* stream);
 
+/* One MARL driver step in ONE launch: `raw` = the actors' tanh outputs [E, V, 2]; the action
+ * mapping of marl_train_bcd.py:1601-1608 (risvec_map_actions) runs in the step kernel's prologue, then Environ.step
+ * (MARL/Environment.py:547-731, no traces: the results are the state views), and marl_get_state of the NEW state
+ * (marl_train_bcd.py:819-827, risvec_observe) is written to `obs` [E, V, 5] in its epilogue.  `arrivals` [E, V] or
+ * NULL (on-device draws).  Bit-identical to the three separate calls.  V <= 8 runs fused (k_marl_v8); other shapes
+ * run the three kernels back to back from this one call. */
+int risvec_step_marl_fused(risvec_env_t* env, const float* raw, const int32_t* partner, const int32_t* ngroups,
+                           const int32_t* arrivals, float* obs, void* stream);
+
 /* Random_phase (MARL:203-206; not called by the shipped drivers): every element gets one of the
  * 2^control_bit quantised angles linspace(0, 2 pi, n, endpoint=False)[k] (:169).  idx [E,M] i32
  * (device) injects the choices k (python `random.choice` in the reference); NULL draws them on the

@@ -310,6 +310,25 @@ class BatchedEnviron:
         ar = self._dev(arrivals, torch.int32, (self.E, self.V))[None] if arrivals is not None else None
         return {k: v[0] for k, v in self.rollout_marl(a[None], partner, ngroups, ar, traces).items()}
 
+    def step_marl_fused(self, raw, partner, ngroups, arrivals=None, obs_out=None):
+        """One driver step in one launch: `raw` = the actors' tanh outputs [E,V,2]; the action
+        mapping (marl_train_bcd.py:1601-1608), Environ.step and marl_get_state (:819-827) of the new state.
+        Returns the observation [E,V,5]; the step's results are the state views (`reward`, `reward_user`, ...)."""
+        if self.variant != "marl":
+            raise ValueError("step_marl_fused is the MARL driver step")
+        r = self._dev(raw, torch.float32, (self.E, self.V, 2))
+        pt = self._dev(partner, torch.int32, (self.E, self.V))
+        ng = self._dev(ngroups, torch.int32, (self.E,))
+        ar = self._dev(arrivals, torch.int32, (self.E, self.V)) if arrivals is not None else None
+        if obs_out is None:
+            obs_out = torch.empty(self.E, self.V, 5, dtype=torch.float32, device=self.device)
+        elif obs_out.dtype != torch.float32 or tuple(obs_out.shape) != (self.E, self.V, 5) or not obs_out.is_contiguous() \
+                or obs_out.device != self.device:
+            raise ValueError(f"obs_out must be a contiguous float32 [{self.E},{self.V},5] tensor on {self.device}")
+        check(self._lib.risvec_step_marl_fused(self._h, self._p(r), self._p(pt), self._p(ng), self._p(ar), self._p(obs_out),
+                                               self.stream))
+        return obs_out
+
     def step_sarl(self, action, phase, arrivals=None, traces=()):
         a = self._dev(action, torch.float32, (self.E, 2, self.V))
         ph = self._dev(phase, torch.float32, (self.E, self.M))

@@ -1130,6 +1130,31 @@ int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float
     return check_launch(env, "k_map_actions_sarl");
 }
 
+int risvec_step_marl_fused(risvec_env_t* env, const float* raw, const int32_t* partner, const int32_t* ngroups,
+                           const int32_t* arrivals, float* obs, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (env->dims.variant != RISVEC_VARIANT_MARL) return fail(RISVEC_ERR_INVALID, "handle is not a MARL env");
+    if (!raw || !partner || !ngroups || !obs) return fail(RISVEC_ERR_INVALID, "raw, partner, ngroups and obs are required");
+    ENTER_DEVICE(env->device);
+    const Dims& d = env->dims;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.V <= 8 && !env->force_generic && (((uintptr_t)raw) & 7u) == 0) {
+        // ONE launch: action mapping in the prologue, Environ.step, marl_get_state of the new state in the epilogue
+        MarlArgs a;
+        memset(&a, 0, sizeof(a));
+        a.T = 1; a.raw = raw; a.obs = obs; a.partner = partner; a.ngroups = ngroups; a.arrivals = arrivals;
+        k_marl_v8<false, false><<<(d.E + 3) / 4, 32, 0, st>>>(d, env->st, env->params, a);
+        return check_step_launch(env, "k_marl_v8");
+    }
+    // shapes the fused kernel does not take: the same three steps as separate launches (scratch action in the stage)
+    if (int rc = ensure_stage(env, (size_t)d.E * 2 * d.V * 4 + 256)) return rc;
+    Carver c{env->stage, 0};
+    float* act = c.take<float>((size_t)d.E * 2 * d.V);
+    if (int rc = risvec_map_actions(env, raw, act, nullptr, stream)) return rc;
+    if (int rc = risvec_rollout_marl(env, 1, act, partner, ngroups, arrivals, nullptr, stream)) return rc;
+    return risvec_observe(env, obs, stream);
+}
+
 int risvec_random_phase(risvec_env_t* env, const int32_t* idx, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     ENTER_DEVICE(env->device);

@@ -23,6 +23,11 @@ struct MarlArgs {
     risvec_marl_out_t out;
     const float* in_rec;   // packed layout: [T,E,RISVEC_MARL_IN_WORDS]  (see include/risvec.h)
     float* out_rec;        // packed layout: [T,E,RISVEC_MARL_OUT_WORDS]
+    // fused driver step (risvec_step_marl_fused; k_marl_v8 only): `raw` = the actors' tanh
+    // outputs [T,E,V,2] mapped in the prologue instead of reading `action`; `obs` [E,V,5] = marl_get_state of the
+    // state after the last step, written in the epilogue
+    const float* raw;
+    float* obs;
 };
 
 struct SarlArgs {
@@ -1200,9 +1205,16 @@ __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t
             in.a1 = __ldg(q + 32);
             in.arr = __ldg(reinterpret_cast<const int*>(q) + 64);
         } else {
-            const float* q = ac_b + (size_t)tc * s2V;
-            in.a0 = act ? __ldg(q) : 0.f;
-            in.a1 = act ? __ldg(q + V) : 0.f;
+            if (!FULL && a.raw != nullptr) {  // action mapping of the driver (marl_train_bcd.py:1601-1608), as k_map_actions_marl
+                const float2 r = act ? __ldg(reinterpret_cast<const float2*>(a.raw) + (size_t)tc * sV + ev) : make_float2(-1.f, -1.f);
+                in.a0 = (fminf(fmaxf(r.x, -0.999f), 0.999f) + 1.f) / 2.f;
+                in.a1 = fmaxf((fminf(fmaxf(r.y, -0.999f), 0.999f) + 1.f) / 2.f, floor_f);
+                if (!act) in.a0 = in.a1 = 0.f;
+            } else {
+                const float* q = ac_b + (size_t)tc * s2V;
+                in.a0 = act ? __ldg(q) : 0.f;
+                in.a1 = act ? __ldg(q + V) : 0.f;
+            }
             in.arr = (act && (FULL || ar_b != nullptr)) ? __ldg(ar_b + (size_t)tc * sV) : 0;
         }
     };
@@ -1355,6 +1367,14 @@ __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t
             s.mecq[e] = Q;
             s.reward[e] = l_glob;
             s.step_ctr[e] = step0 + T;
+        }
+        if (!FULL && a.obs != nullptr) {  // marl_get_state of the new state (marl_train_bcd.py:819-827), as k_observe
+            float* o = a.obs + ev * 5;
+            o[0] = (float)(buf / 10.0);
+            o[1] = l_dt / 10.f;
+            o[2] = l_dp / 10.f;
+            o[3] = s.over_data[ev] / 10.f;
+            o[4] = l_rate / 20.f;
         }
     }
 }

@@ -446,3 +446,34 @@ def test_shared_statistics_accumulator_single_process():
     total = shared.read()
     assert torch.equal(total, 2.0 * local.cpu()) and float(total[NSTAT]) != 0.0
     shared.close()
+
+
+@pytest.mark.parametrize("V,inject", [(8, True), (8, False), (5, True), (12, True)])
+def test_fused_driver_step_is_bit_identical_to_the_three_calls(V, inject):
+    """risvec_step_marl_fused (action mapping in the step kernel's prologue, observation in
+    its epilogue) against map_actions -> step_marl -> observe on a twin env: every state view and the observation
+    are bit-identical over several steps (V = 12: the shapes the fused kernel does not take run the three kernels
+    from the one call)."""
+    from ris_vec_marl_b200 import BatchedEnviron, encode_groups, marl_yaml_overrides
+
+    E, M = 130, 40
+    envs = [BatchedEnviron("marl", E, V, M, seed=11, **marl_yaml_overrides()) for _ in range(2)]
+    for env in envs:
+        env.make_new_game(); env.renew_positions(); env.compute_parms(); env.optimize_phase_shift(); env.update_channel_gains()
+    groups = [[i, i + 1] for i in range(0, V - 2, 2)] + [[V - 1]]
+    part, ng = encode_groups(groups, V)
+    partner = torch.as_tensor(np.tile(part, (E, 1))).cuda()
+    ngroups = torch.full((E,), ng, dtype=torch.int32, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(5):
+        raw = torch.rand(E, V, 2, device="cuda", generator=g) * 2.2 - 1.1   # beyond [-1, 1]: the clip is exercised
+        arr = torch.poisson(torch.full((E, V), 1.0, device="cuda"), generator=g).to(torch.int32) if inject else None
+        a, b = envs
+        obs_a = a.step_marl_fused(raw, partner, ngroups, arr)
+        b.step_marl(b.map_actions(raw), partner, ngroups, arr)
+        obs_b = b.observe()
+        assert torch.equal(obs_a, obs_b), f"observation differs at step {step}"
+        for name in ("DataBuf", "data_t", "data_p", "vehicle_rate", "reward", "reward_user", "over_power", "mec_queue_cycles", "stats", "last_power_W", "data_r"):
+            va, vb = getattr(a, name), getattr(b, name)
+            assert torch.equal(va, vb), f"{name} differs at step {step}"
+    assert envs[0].last_kernel() == ("k_marl_v8" if V <= 8 else "k_marl_rollout")

@@ -74,27 +74,30 @@ def driver_loop(envs, steps, driver, actor_dtype, rank, world, local, ranks=None
         frozen = torch.ones(E, dtype=torch.int32, device=dev)
         ctr = [0]
 
+    bufs = [obs, obs2]  # the fused step writes the next observation: the two buffers alternate
+    env.observe(out=bufs[0])
+
     def driver_step():
         first = ctr[0] % 100 == 0
         ctr[0] += 1
-        env.observe(out=obs)
-        x = obs.to(torch.bfloat16) if actor_dtype == "bf16" else obs
+        cur, nxt = bufs[0], bufs[1]
+        x = cur.to(torch.bfloat16) if actor_dtype == "bf16" else cur
         raw = actors(x).float()
-        act = env.map_actions(raw)
+        act = env.map_actions(raw)      # the pairing stage reads the mapped offload power
         part_v, ng_v = env.pair_noma(act, K, q, recalc_mask=first, reuse=None if first else frozen, new_episode=first)
         probs = actors.intent(env.pair_mask)
-        env.step_marl(act, part_v, ng_v)
-        env.observe(out=obs2)
-        rb.store_marl(obs, probs, raw, env.reward, env.reward_user, obs2, done=(ctr[0] % 100 == 0),
+        env.step_marl_fused(raw, part_v, ng_v, obs_out=nxt)   # mapping + Environ.step + marl_get_state: one launch
+        rb.store_marl(cur, probs, raw, env.reward, env.reward_user, nxt, done=(ctr[0] % 100 == 0),
                       mask_u8=env.pair_mask)
+        bufs[0], bufs[1] = nxt, cur
 
     def step():
         if driver:
             return driver_step()
-        env.observe(out=obs)
-        x = obs.to(torch.bfloat16) if actor_dtype == "bf16" else obs
-        act = env.map_actions(actors(x).float())
-        env.step_marl(act, partner, ngroups)  # arrivals: on-device Philox
+        cur, nxt = bufs[0], bufs[1]
+        x = cur.to(torch.bfloat16) if actor_dtype == "bf16" else cur
+        env.step_marl_fused(actors(x).float(), partner, ngroups, obs_out=nxt)  # arrivals: on-device Philox
+        bufs[0], bufs[1] = nxt, cur
 
     for _ in range(5):
         step()
@@ -111,9 +114,10 @@ def driver_loop(envs, steps, driver, actor_dtype, rank, world, local, ranks=None
     if ranks is not None:
         sec = ranks.max(sec)
     res = {"envs_per_gpu": E, "V": V, "M": M, "steps": steps, "actor": "8 x MLP 5-512-256-{2, V} (bmm), " + actor_dtype,
-           "loop": ("observe, actors + intent head (torch), map_actions, NOMA pairing (solve on step 0 of each 100-step "
-                    "episode, frozen after), Environ.step (" + env.last_kernel() + "), observe, replay write")
-                   if driver else "observe, actors (torch), map_actions, Environ.step",
+           "loop": ("actors + intent head (torch), map_actions (for the pairing), NOMA pairing (solve on step 0 of each "
+                    "100-step episode, frozen after), fused [action mapping + Environ.step + observation] (" +
+                    env.last_kernel() + "), replay write")
+                   if driver else "actors (torch), fused [action mapping + Environ.step + observation] (" + env.last_kernel() + ")",
            "value": world * E * steps / sec, "unit": "env-steps/s", "us_per_step": sec / steps * 1e6}
     if driver:
         res["replay_rows"] = int(rb.mem_cntr)
@@ -159,27 +163,30 @@ def main():
         frozen = torch.ones(E, dtype=torch.int32, device=dev)
         ctr = [0]
 
+    bufs = [obs, obs2]  # the fused step writes the next observation: the two buffers alternate
+    env.observe(out=bufs[0])
+
     def driver_step():
         first = ctr[0] % 100 == 0
         ctr[0] += 1
-        env.observe(out=obs)
-        x = obs.to(torch.bfloat16) if a.actor_dtype == "bf16" else obs
+        cur, nxt = bufs[0], bufs[1]
+        x = cur.to(torch.bfloat16) if a.actor_dtype == "bf16" else cur
         raw = actors(x).float()
-        act = env.map_actions(raw)
+        act = env.map_actions(raw)      # the pairing stage reads the mapped offload power
         part_v, ng_v = env.pair_noma(act, K, q, recalc_mask=first, reuse=None if first else frozen, new_episode=first)
         probs = actors.intent(env.pair_mask)
-        env.step_marl(act, part_v, ng_v)
-        env.observe(out=obs2)
-        rb.store_marl(obs, probs, raw, env.reward, env.reward_user, obs2, done=(ctr[0] % 100 == 0),
+        env.step_marl_fused(raw, part_v, ng_v, obs_out=nxt)   # mapping + Environ.step + marl_get_state: one launch
+        rb.store_marl(cur, probs, raw, env.reward, env.reward_user, nxt, done=(ctr[0] % 100 == 0),
                       mask_u8=env.pair_mask)
+        bufs[0], bufs[1] = nxt, cur
 
     def step():
         if a.driver:
             return driver_step()
-        env.observe(out=obs)
-        x = obs.to(torch.bfloat16) if a.actor_dtype == "bf16" else obs
-        act = env.map_actions(actors(x).float())
-        env.step_marl(act, partner, ngroups)  # arrivals: on-device Philox
+        cur, nxt = bufs[0], bufs[1]
+        x = cur.to(torch.bfloat16) if a.actor_dtype == "bf16" else cur
+        env.step_marl_fused(actors(x).float(), partner, ngroups, obs_out=nxt)  # arrivals: on-device Philox
+        bufs[0], bufs[1] = nxt, cur
 
     def timed(fn, n):
         torch.cuda.synchronize()
@@ -209,13 +216,13 @@ def main():
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
-            step()
+            step(); step()
             torch.cuda.synchronize()
             with torch.cuda.graph(g, stream=s):
-                step()
-        sec = timed(g.replay, a.steps)
-        res["graph_env_steps_per_s"] = world * E * a.steps / sec
-        res["graph_us_per_step"] = sec / a.steps * 1e6
+                step(); step()   # the two observation buffers alternate: one replay = two steps
+        sec = timed(g.replay, a.steps // 2)
+        res["graph_env_steps_per_s"] = world * E * (a.steps // 2) * 2 / sec
+        res["graph_us_per_step"] = sec / ((a.steps // 2) * 2) * 1e6
     except Exception as exc:  # capture is best-effort
         res["graph_error"] = repr(exc)[:200]
     if a.driver:

@@ -267,6 +267,11 @@ int risvec_map_actions(risvec_env_t* env, const float* raw, float* action, float
  * run the three kernels back to back from this one call. */
 int risvec_step_marl_fused(risvec_env_t* env, const float* raw, const int32_t* partner, const int32_t* ngroups,
                            const int32_t* arrivals, float* obs, void* stream);
+/* The SARL driver step in one launch: `raw` = the actor's tanh outputs [E, 2V + M] (power rows, then the RIS phases);
+ * the mapping of ddpg_train.py:151-160, Environ.step (SARL/Environment.py:321-359) and get_state of the new state
+ * (ddpg_train.py:47-73) -> `obs` [E, V, M / V + 5].  Fused for V <= 8, M even <= 64 (k_sarl_mma); other shapes run
+ * the three kernels back to back from this one call.  Bit-identical to the three separate calls. */
+int risvec_step_sarl_fused(risvec_env_t* env, const float* raw, const int32_t* arrivals, float* obs, void* stream);
 
 /* Random_phase (MARL:203-206; not called by the shipped drivers): every element gets one of the
  * 2^control_bit quantised angles linspace(0, 2 pi, n, endpoint=False)[k] (:169).  idx [E,M] i32

@@ -329,6 +329,23 @@ class BatchedEnviron:
                                                self.stream))
         return obs_out
 
+    def step_sarl_fused(self, raw, arrivals=None, obs_out=None):
+        """The SARL driver step in one launch: `raw` = the actor's tanh outputs [E, 2V+M]; the mapping of
+        ddpg_train.py:151-160, Environ.step and get_state (:47-73) of the new state.  Returns the observation
+        [E, V, M//V + 5]; the step's results are the state views."""
+        if self.variant != "sarl":
+            raise ValueError("step_sarl_fused is the SARL driver step")
+        r = self._dev(raw, torch.float32, (self.E, 2 * self.V + self.M))
+        ar = self._dev(arrivals, torch.int32, (self.E, self.V)) if arrivals is not None else None
+        W = self.M // self.V + 5
+        if obs_out is None:
+            obs_out = torch.empty(self.E, self.V, W, dtype=torch.float32, device=self.device)
+        elif obs_out.dtype != torch.float32 or tuple(obs_out.shape) != (self.E, self.V, W) or not obs_out.is_contiguous() \
+                or obs_out.device != self.device:
+            raise ValueError(f"obs_out must be a contiguous float32 [{self.E},{self.V},{W}] tensor on {self.device}")
+        check(self._lib.risvec_step_sarl_fused(self._h, self._p(r), self._p(ar), self._p(obs_out), self.stream))
+        return obs_out
+
     def step_sarl(self, action, phase, arrivals=None, traces=()):
         a = self._dev(action, torch.float32, (self.E, 2, self.V))
         ph = self._dev(phase, torch.float32, (self.E, self.M))

@@ -1143,7 +1143,7 @@ int risvec_step_marl_fused(risvec_env_t* env, const float* raw, const int32_t* p
         MarlArgs a;
         memset(&a, 0, sizeof(a));
         a.T = 1; a.raw = raw; a.obs = obs; a.partner = partner; a.ngroups = ngroups; a.arrivals = arrivals;
-        k_marl_v8<false, false><<<(d.E + 3) / 4, 32, 0, st>>>(d, env->st, env->params, a);
+        k_marl_v8<false, false, false, true><<<(d.E + 3) / 4, 32, 0, st>>>(d, env->st, env->params, a);
         return check_step_launch(env, "k_marl_v8");
     }
     // shapes the fused kernel does not take: the same three steps as separate launches (scratch action in the stage)
@@ -1152,6 +1152,37 @@ int risvec_step_marl_fused(risvec_env_t* env, const float* raw, const int32_t* p
     float* act = c.take<float>((size_t)d.E * 2 * d.V);
     if (int rc = risvec_map_actions(env, raw, act, nullptr, stream)) return rc;
     if (int rc = risvec_rollout_marl(env, 1, act, partner, ngroups, arrivals, nullptr, stream)) return rc;
+    return risvec_observe(env, obs, stream);
+}
+
+int risvec_step_sarl_fused(risvec_env_t* env, const float* raw, const int32_t* arrivals, float* obs, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (env->dims.variant != RISVEC_VARIANT_SARL) return fail(RISVEC_ERR_INVALID, "handle is not a SARL env");
+    if (!raw || !obs) return fail(RISVEC_ERR_INVALID, "raw and obs are required");
+    ENTER_DEVICE(env->device);
+    const Dims& d = env->dims;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool mma_ok = !env->force_generic && (env->sarl_path == 0 || env->sarl_path == 1) && sarl_mma_covers(env);
+    if (mma_ok && (((uintptr_t)raw) & 7u) == 0) {
+        // ONE launch: action mapping in the prologue, Environ.step, get_state of the new state in the epilogue
+        SarlArgs a;
+        memset(&a, 0, sizeof(a));
+        a.T = 1; a.raw = raw; a.obs = obs; a.arrivals = arrivals;
+        const int M = d.M, blocks = (d.E + 3) / 4;
+        if (M <= 8) k_sarl_mma<1, false, true><<<blocks, 128, 0, st>>>(d, env->st, env->params, a);
+        else if (M <= 16) k_sarl_mma<2, false, true><<<blocks, 128, 0, st>>>(d, env->st, env->params, a);
+        else if (M <= 24) k_sarl_mma<3, false, true><<<blocks, 128, 0, st>>>(d, env->st, env->params, a);
+        else if (M <= 40) k_sarl_mma<5, false, true><<<blocks, 128, 0, st>>>(d, env->st, env->params, a);
+        else k_sarl_mma<8, false, true><<<blocks, 128, 0, st>>>(d, env->st, env->params, a);
+        return check_step_launch(env, "k_sarl_mma");
+    }
+    // shapes the fused kernel does not take: the same three steps as separate launches (scratch in the stage)
+    if (int rc = ensure_stage(env, (size_t)d.E * (2 * d.V + d.M) * 4 + 512)) return rc;
+    Carver c{env->stage, 0};
+    float* act = c.take<float>((size_t)d.E * 2 * d.V);
+    float* ph = c.take<float>((size_t)d.E * d.M);
+    if (int rc = risvec_map_actions(env, raw, act, ph, stream)) return rc;
+    if (int rc = risvec_rollout_sarl(env, 1, act, ph, arrivals, nullptr, stream)) return rc;
     return risvec_observe(env, obs, stream);
 }
 

@@ -63,8 +63,10 @@ struct SarlMmaIn {     // inputs of one 8-step tile, as one lane needs them
 
 // KT = k-tiles of 8 RIS elements (M <= 8 KT, M even); FULL = V == 8, M == 8 KT, every trace and the
 // arrivals supplied (no per-access predicates).  Block = 4 warps = 4 adjacent envs.
-template <int KT, bool FULL>
+// FUSED = the one-launch driver step (risvec_step_sarl_fused): inputs from the actor's raw row, observation out
+template <int KT, bool FULL, bool FUSED = false>
 __global__ void __launch_bounds__(128, 4) k_sarl_mma(Dims d, State s, risvec_params_t p, SarlArgs a) {
+    static_assert(!(FULL && FUSED), "the fused driver step is a variant of the generic form");
     const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
     const int E = d.E, V = d.V, M = d.M, T = a.T;
     const int e = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -111,7 +113,22 @@ __global__ void __launch_bounds__(128, 4) k_sarl_mma(Dims d, State s, risvec_par
     const int* const ar_b = (FULL || a.arrivals != nullptr) ? a.arrivals + ev : nullptr;
     const int Tm1 = T - 1;
 
+    // fused driver step: the action mapping of ddpg_train.py:151-160 (k_map_actions_sarl) applied to the raw row
+    constexpr bool fused = FUSED;
+    const size_t sW = (size_t)E * (2 * V + M);
+    const float* const raw_e = fused ? a.raw + (size_t)e * (2 * V + M) : nullptr;  // + t sW: [power 2V | phase M]
+    auto map01 = [](float r) { return (fminf(fmaxf(r, -0.999f), 0.999f) + 1.f) / 2.f; };
+    auto map_phase = [&](float r) { return map01(r) * 3.14159265358979323846f * 2.f; };
     auto load_phases = [&](float2 (&ph)[KT], int t0) {
+        if (fused) {
+            const float* q = raw_e + (size_t)min(t0 + g, Tm1) * sW + 2 * V + 2 * tig;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const float2 r = (8 * j + 2 * tig < M) ? __ldg(reinterpret_cast<const float2*>(q + 8 * j)) : make_float2(-1.f, -1.f);
+                ph[j] = make_float2(map_phase(r.x), map_phase(r.y));
+            }
+            return;
+        }
         const float* q = ph_b + (size_t)min(t0 + g, Tm1) * sM;  // B fragment column g = step t0 + g
 #pragma unroll
         for (int j = 0; j < KT; ++j)
@@ -122,13 +139,19 @@ __global__ void __launch_bounds__(128, 4) k_sarl_mma(Dims d, State s, risvec_par
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const size_t t = (size_t)min(t0 + 2 * tig + i, Tm1);
-            in.a0[i] = __ldg(ac_b + t * s2V);
-            in.a1[i] = __ldg(ac_b + t * s2V + V);
+            if (fused) {
+                in.a0[i] = map01(__ldg(raw_e + t * sW + vc));
+                in.a1[i] = map01(__ldg(raw_e + t * sW + V + vc));
+            } else {
+                in.a0[i] = __ldg(ac_b + t * s2V);
+                in.a1[i] = __ldg(ac_b + t * s2V + V);
+            }
             in.arr[i] = (FULL || ar_b != nullptr) ? __ldg(ar_b + t * sV) : 0;
         }
     };
     // L2 prefetch of the env's rows of a later tile: lane (g, tig) covers sectors of row t0 + g
     auto prefetch_tile = [&](int t0) {
+        if (fused) return;  // one step: nothing to pull ahead
         const size_t t = (size_t)min(t0 + g, Tm1);
         const float* q = a.phase + t * sM + (size_t)e * M + tig * 8;  // M <= 64: at most two sectors per lane
         if (FULL || tig * 8 < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
@@ -247,8 +270,22 @@ __global__ void __launch_bounds__(128, 4) k_sarl_mma(Dims d, State s, risvec_par
 
     // ---- registers -> state (what the reference object holds after the last step)
     for (int m = lane; m < M; m += 32)  // elements_phase_shift_real = the last action_phase (SARL:128)
-        s.phase_real[(size_t)e * M + m] = __ldg(a.phase + (size_t)Tm1 * sM + (size_t)e * M + m);
+        s.phase_real[(size_t)e * M + m] = fused ? map_phase(__ldg(raw_e + (size_t)Tm1 * sW + 2 * V + m))
+                                                : __ldg(a.phase + (size_t)Tm1 * sM + (size_t)e * M + m);
     const int last = Tm1 & 7;  // position of step T - 1 in its tile: lane tig = last / 2, slot last % 2
+    if (fused && a.obs != nullptr && vact) {  // get_state of the new state (ddpg_train.py:47-73), as k_observe
+        const int n_theta = M / V, W = n_theta + 5;
+        float* o = a.obs + ev * W;
+        for (int k = tig; k < n_theta; k += 4) o[k] = map_phase(__ldg(raw_e + (size_t)Tm1 * sW + 2 * V + g * n_theta + k));
+        if (tig == (last >> 1)) {
+            const int i = last & 1;
+            o[n_theta + 0] = (float)(buf / 10.0);
+            o[n_theta + 1] = (i ? o_dt[1] : o_dt[0]) / 10.f;
+            o[n_theta + 2] = (i ? o_dp[1] : o_dp[0]) / 10.f;
+            o[n_theta + 3] = (i ? o_overd[1] : o_overd[0]) / 10.f;
+            o[n_theta + 4] = (i ? o_rate[1] : o_rate[0]) / 20.f;
+        }
+    }
     if (tig == (last >> 1) && vact) {
         const int i = last & 1;
         s.databuf[ev] = buf;

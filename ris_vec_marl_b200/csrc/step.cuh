@@ -40,6 +40,11 @@ struct SarlArgs {
     float* out_rec;       // packed layout: [T,E,RISVEC_SARL_OUT_WORDS]
     float* g2;            // [T,E,V] scratch |S_v|^2 between the cascade and scan kernels (large M)
     int t_chunk;          // steps per block of the cascade kernel (even)
+    // fused driver step (risvec_step_sarl_fused; k_sarl_mma only): `raw` = the actor's tanh
+    // outputs [T,E,2V+M] mapped in the prologue instead of reading `action` / `phase`; `obs` [E,V,M/V+5] =
+    // get_state of the state after the last step, written in the epilogue
+    const float* raw;
+    float* obs;
 };
 
 __device__ inline int draw_arrival(const Dims& d, int e, int v, long long step, float lam) {
@@ -1129,8 +1134,10 @@ struct MarlHeavy {
     double f_local, cap;
 };
 
-template <bool FULL, bool PACKED, bool ALLACT = PACKED>
+// FUSED = the one-launch driver step (risvec_step_marl_fused): actions from the actors' raw outputs, observation out
+template <bool FULL, bool PACKED, bool ALLACT = PACKED, bool FUSED = false>
 __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t p, MarlArgs a) {
+    static_assert(!FUSED || (!FULL && !PACKED), "the fused driver step is a variant of the generic form");
     static_assert(!PACKED || (FULL && ALLACT), "the packed record layout carries every stream");
     constexpr int RIN = RISVEC_MARL_IN_WORDS, ROUT = RISVEC_MARL_OUT_WORDS;
     const int lane = threadIdx.x & 31, el = lane >> 3, v = lane & 7;
@@ -1205,7 +1212,7 @@ __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t
             in.a1 = __ldg(q + 32);
             in.arr = __ldg(reinterpret_cast<const int*>(q) + 64);
         } else {
-            if (!FULL && a.raw != nullptr) {  // action mapping of the driver (marl_train_bcd.py:1601-1608), as k_map_actions_marl
+            if (FUSED) {  // action mapping of the driver (marl_train_bcd.py:1601-1608), as k_map_actions_marl
                 const float2 r = act ? __ldg(reinterpret_cast<const float2*>(a.raw) + (size_t)tc * sV + ev) : make_float2(-1.f, -1.f);
                 in.a0 = (fminf(fmaxf(r.x, -0.999f), 0.999f) + 1.f) / 2.f;
                 in.a1 = fmaxf((fminf(fmaxf(r.y, -0.999f), 0.999f) + 1.f) / 2.f, floor_f);
@@ -1368,7 +1375,7 @@ __global__ void __launch_bounds__(32) k_marl_v8(Dims d, State s, risvec_params_t
             s.reward[e] = l_glob;
             s.step_ctr[e] = step0 + T;
         }
-        if (!FULL && a.obs != nullptr) {  // marl_get_state of the new state (marl_train_bcd.py:819-827), as k_observe
+        if (FUSED && a.obs != nullptr) {  // marl_get_state of the new state (marl_train_bcd.py:819-827), as k_observe
             float* o = a.obs + ev * 5;
             o[0] = (float)(buf / 10.0);
             o[1] = l_dt / 10.f;

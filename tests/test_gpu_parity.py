@@ -477,3 +477,29 @@ def test_fused_driver_step_is_bit_identical_to_the_three_calls(V, inject):
             va, vb = getattr(a, name), getattr(b, name)
             assert torch.equal(va, vb), f"{name} differs at step {step}"
     assert envs[0].last_kernel() == ("k_marl_v8" if V <= 8 else "k_marl_rollout")
+
+
+@pytest.mark.parametrize("V,M,inject", [(8, 40, True), (8, 40, False), (5, 30, True), (8, 64, True), (12, 48, True)])
+def test_fused_sarl_driver_step_is_bit_identical_to_the_three_calls(V, M, inject):
+    """risvec_step_sarl_fused against map_actions -> step_sarl -> observe on a twin env ((12, 48): a shape the
+    fused kernel does not take runs the three kernels from the one call)."""
+    from ris_vec_marl_b200 import BatchedEnviron
+    from tests.gpu_backend import sarl_path
+
+    E = 70
+    with sarl_path("mma"):   # both twins on the tensor-core kernel (the fused form lives in k_sarl_mma)
+        envs = [BatchedEnviron("sarl", E, V, M, seed=21) for _ in range(2)]
+    for env in envs:
+        env.make_new_game(); env.renew_positions(); env.compute_parms()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for step in range(5):
+        raw = torch.rand(E, 2 * V + M, device="cuda", generator=g) * 2.2 - 1.1
+        arr = torch.poisson(torch.full((E, V), 3.0, device="cuda"), generator=g).to(torch.int32) if inject else None
+        a, b = envs
+        obs_a = a.step_sarl_fused(raw, arr)
+        act, ph = b.map_actions(raw)
+        b.step_sarl(act, ph, arr)
+        obs_b = b.observe()
+        assert torch.equal(obs_a, obs_b), f"observation differs at step {step}: {(obs_a - obs_b).abs().max()}"
+        for name in ("DataBuf", "data_t", "data_p", "vehicle_rate", "reward", "over_power", "over_data", "phase_real", "data_r"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"{name} differs at step {step}"

@@ -1453,6 +1453,15 @@ int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* 
     return RISVEC_OK;
 }
 
+}  // extern "C"
+namespace risvec {
+__global__ void k_atomic_add_f64(double* __restrict__ dst, const double* __restrict__ src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(dst + i, src[i]);    // dst may be peer memory: a red.global.add.f64 over NVLink
+}
+}  // namespace risvec
+extern "C" {
+
 int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream) {
     if (!env || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
     ENTER_DEVICE(env->device);
@@ -1490,10 +1499,6 @@ int risvec_shared_buffer_open(int device, const unsigned char ipc_handle[64], vo
     CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     *dev_ptr = p;
     return RISVEC_OK;
-}
-__global__ void k_atomic_add_f64(double* __restrict__ dst, const double* __restrict__ src, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(dst + i, src[i]);    // dst may be peer memory: a red.global.add.f64 over NVLink
 }
 int risvec_shared_buffer_add(int device, double* dst, const double* src, int n, void* stream) {
     if (!dst || !src || n <= 0) return fail(RISVEC_ERR_INVALID, "bad arguments");

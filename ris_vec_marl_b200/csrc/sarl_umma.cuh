@@ -32,8 +32,11 @@
 // stage 1.7 us later, then one stage per 1.5 us, 1.7 us from the last "D full" to the end of the block: 33 us per
 // env.  The steady state is bound by the tensor core's DISPATCH of these small instructions: 32 per stage take
 // 1.44 us (~83 clocks each, where the datapath needs 16) -- the same with N = 64 per instruction (timing
-// experiment) and the same with two alternating accumulator chains, so it is neither operand bandwidth nor the
-// accumulate dependency.  (History: with A in shared memory an instruction took ~128 clocks, three M = 64,
+// experiment) and the same with two alternating accumulator chains: the instruction time follows the bytes of
+// operand A (shared memory, unswizzled: ~32 B per clock; tensor memory: ~50-64 B per clock), not N.  A variant
+// with 32-step stages (N = 64: half the instructions per step, both step-warp sets on one accumulator) was
+// correct but slower (0.249 ms): the two sets then run in lock-step, and a set needs ~2.8 us per 16-step
+// stage -- the step warps, two sets of four, are the other limit of the steady state.  (History: with A in shared memory an instruction took ~128 clocks, three M = 64,
 // N = 16 instructions per k-step ~62 clocks each.)
 #pragma once
 #include "sarl_mma.cuh"

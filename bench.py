@@ -228,8 +228,9 @@ def workload_config(args, world=1):
             "envs_per_gpu": args.envs, "V": args.V, "M": args.M, "T": args.T,
             "layout": "the reference's own array layout: action [T,E,2,V] f32, phase [T,E,M] f32, arrivals [T,E,V] i32 "
                       "in; one [T,E,V] f32 array per trace + reward [T,E] out (no packing / conversion pass anywhere)",
-            "stats_interval": f"statistics interval = the timed region ({args.steps} rollouts x {args.T} steps); "
-                              "k_shard_stats runs after every rollout, inside the timed region",
+            "stats_interval": f"statistics interval = the timed region ({args.steps} rollouts x {args.T} steps); every "
+                              "rollout adds its last step's statistics to the attached accumulator in the kernel's "
+                              "tail, one collect per interval, all inside the timed region",
             "l2_policy": "inputs+outputs of one launch exceed the 126 MB L2; nothing is re-read between launches"}
 
 
@@ -465,10 +466,18 @@ def main():
                       "launch): no collective, no rank waits for another; totals read after the end barrier"
                       if shared is not None else "one NCCL all-reduce of the 17-entry vector per timed region")
 
-    def episode_stats():  # per-rollout statistics: one tiny kernel, no collective
-        env.shard_stats(out=stats_sum, accumulate=True)
+    # per-rollout statistics: folded into the rollout kernel's tail (risvec_attach_stats_accumulator), no separate pass
+    # (RISVEC_BENCH_FOLD=0: the separate k_shard_stats launch after every rollout, for A/B runs)
+    fold = os.environ.get("RISVEC_BENCH_FOLD", "1") != "0"
+    env.attach_stats_accumulator(fold)
+
+    def episode_stats():
+        if not fold:
+            env.shard_stats(out=stats_sum, accumulate=True)
 
     def reduce_stats():   # the only exchange on the path: once per statistics interval
+        if fold:
+            env.collect_stats(out=stats_sum, accumulate=True)
         if shared is not None:
             shared.add_(stats_sum)
         elif world > 1:
@@ -491,6 +500,8 @@ def main():
             if sampler.lines or sampler.proc is None or time.time() - t_spin > 3.0:
                 break
         sampler.lines.clear()
+    if fold:
+        env.collect_stats()  # discard what the warm-up rollouts accumulated
     stats_sum.zero_()
     if shared is not None:
         shared.zero_()

@@ -373,6 +373,17 @@ int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* 
  * to out [RISVEC_NSTAT + 1] f64 (device). */
 int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream);
 
+/* Statistics WITHOUT a separate pass per rollout.  `slots` = RISVEC_STAT_SLOTS (64) x 32 float64 (256-byte aligned,
+ * zeroed by the caller), 17 used per slot.  Once attached, every risvec_rollout_sarl / _marl (and their _host forms:
+ * the last chunk) adds the per-env statistics of its LAST step -- exactly what risvec_shard_stats would sum right
+ * after it -- into the slots: the tensor-core rollouts (k_sarl_mma_tma, k_marl_tma) do it in their last instructions
+ * (one float64 atomic per block and statistic, slot = block index % 64, so concurrent blocks hit different L2
+ * lines); every other kernel is followed by one k_shard_stats launch into slot 0.  NULL detaches.
+ * risvec_collect_stats: out[17] (+)= the sum over the slots, which are cleared (once per statistics interval). */
+#define RISVEC_STAT_SLOTS 64
+int risvec_attach_stats_accumulator(risvec_env_t* env, double* slots);
+int risvec_collect_stats(risvec_env_t* env, double* slots, double* out, int accumulate, void* stream);
+
 /* Statistics reduction WITHOUT a collective (one node, NVLink / NVSwitch): one rank creates a small device buffer
  * and publishes its 64-byte CUDA IPC handle; every other rank (= process) maps it and passes the mapped pointer as
  * `out` of risvec_shard_stats(accumulate != 0).  k_shard_stats then adds the shard's sums into the owner's HBM with

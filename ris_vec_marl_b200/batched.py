@@ -502,6 +502,27 @@ class BatchedEnviron:
         check(self._lib.risvec_shard_stats(self._h, self._p(out), 1 if accumulate else 0, self.stream))
         return out
 
+    def attach_stats_accumulator(self, attach=True):
+        """From now on every `rollout_sarl` / `rollout_marl` (and `_host`) call adds the statistics of its last step --
+        what `shard_stats` would sum right after it -- into a device accumulator: no separate pass per rollout
+        (the tensor-core rollouts do it in their last instructions).  `collect_stats()` returns and clears the sums."""
+        if attach:
+            self._stat_slots = torch.zeros(64, 32, dtype=torch.float64, device=self.device)
+            check(self._lib.risvec_attach_stats_accumulator(self._h, self._p(self._stat_slots)))
+        else:
+            check(self._lib.risvec_attach_stats_accumulator(self._h, self._p(None)))
+            self._stat_slots = None
+
+    def collect_stats(self, out=None, accumulate=False):
+        """f64 [NSTAT + 1] sums accumulated since the last collect (written or, `accumulate=True`, added to `out`)."""
+        if getattr(self, "_stat_slots", None) is None:
+            raise RuntimeError("attach_stats_accumulator() first")
+        if out is None:
+            out = torch.empty(NSTAT + 1, dtype=torch.float64, device=self.device)
+            accumulate = False
+        check(self._lib.risvec_collect_stats(self._h, self._p(self._stat_slots), self._p(out), 1 if accumulate else 0, self.stream))
+        return out
+
     def state_dict(self):
         """Everything a resumed run needs to CONTINUE this one: the state arena, the host-side call counters
         that key the on-device Philox draws, the scalar parameters and the pairing knobs."""

@@ -340,6 +340,23 @@ __global__ void __launch_bounds__(128, 4)
             s.step_ctr[e] += T;
         }
     }
+    if (a.stats_slots != nullptr) {  // the statistics pass folded in: what k_shard_stats would sum after this launch
+        __shared__ float blk_stat[4][RISVEC_NSTAT + 1];
+        if (mine) {
+            const float vals[RISVEC_NSTAT] = {m_delay, m_energy, m_dl, m_dq, m_dc, m_ttx, m_back, fin.served_frac, m_util, m_viol,
+                                              s_off, s_loc, (float)Q, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int col = 0; col < RISVEC_NSTAT; ++col)
+                if ((col & 7) == g) blk_stat[warp][col] = vals[col];
+            if (g == 0) blk_stat[warp][RISVEC_NSTAT] = fin.glob;
+        }
+        __syncthreads();
+        if (threadIdx.x <= RISVEC_NSTAT) {
+            const int c2 = threadIdx.x;
+            atomicAdd(a.stats_slots + (blockIdx.x % kRisvecStatSlots) * 32 + c2,
+                      ((double)blk_stat[0][c2] + (double)blk_stat[1][c2]) + ((double)blk_stat[2][c2] + (double)blk_stat[3][c2]));
+        }
+    }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
 }
 

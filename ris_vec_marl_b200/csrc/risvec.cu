@@ -94,6 +94,8 @@ struct risvec_env {
     int sarl_tma;       // RISVEC_SARL_TMA = 0 keeps the mma path on its LDG kernel (tests / A-B runs)
     int marl_tma;       // RISVEC_MARL_PATH = v8 keeps the MARL fast path on k_marl_v8 (tests / A-B runs)
     const char* step_kernel;  // name of the kernel(s) the latest rollout launched (risvec_last_step_kernel)
+    double* stats_slots;      // attached statistics accumulator (risvec_attach_stats_accumulator) or null
+    int stats_folded;         // the latest rollout kernel added its statistics itself
 };
 
 struct risvec_replay {
@@ -293,7 +295,10 @@ int launch_sarl_mma_tma(risvec_env* env, const SarlArgs& a, cudaStream_t st, boo
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    kern<<<E / 4, 128, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm_ph, tm_ac, tm_ar, tm_out);
+    SarlArgs af = a;
+    af.stats_slots = env->stats_slots;  // the statistics pass rides in the kernel's tail
+    env->stats_folded = env->stats_slots != nullptr;
+    kern<<<E / 4, 128, smem, st>>>(env->dims, env->st, sarl_consts(env->params), af, tm_ph, tm_ac, tm_ar, tm_out);
     *launched = true;
     return check_step_launch(env, "k_sarl_mma_tma");
 }
@@ -723,8 +728,31 @@ int risvec_update_channel_gains(risvec_env_t* env, const double* chan_rand, cons
     return check_launch(env, "k_gains_3gpp");
 }
 
+// statistics accumulator attached: kernels that fold the statistics pass set env->stats_folded, every other kernel
+// is followed by k_shard_stats into slot 0
+static int rollout_marl_impl(risvec_env_t* env, int T, const float* action, const int32_t* partner, const int32_t* ngroups,
+                             const int32_t* arrivals, const risvec_marl_out_t* out, void* stream);
+static int rollout_sarl_impl(risvec_env_t* env, int T, const float* action, const float* phase, const int32_t* arrivals,
+                             const risvec_sarl_out_t* out, void* stream);
+static int finish_rollout(risvec_env_t* env, int rc, void* stream) {
+    if (rc == RISVEC_OK && env->stats_slots != nullptr && !env->stats_folded) rc = risvec_shard_stats(env, env->stats_slots, 1, stream);
+    return rc;
+}
 int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int32_t* partner, const int32_t* ngroups,
                         const int32_t* arrivals, const risvec_marl_out_t* out, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    env->stats_folded = 0;
+    return finish_rollout(env, rollout_marl_impl(env, T, action, partner, ngroups, arrivals, out, stream), stream);
+}
+int risvec_rollout_sarl(risvec_env_t* env, int T, const float* action, const float* phase, const int32_t* arrivals,
+                        const risvec_sarl_out_t* out, void* stream) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    env->stats_folded = 0;
+    return finish_rollout(env, rollout_sarl_impl(env, T, action, phase, arrivals, out, stream), stream);
+}
+
+static int rollout_marl_impl(risvec_env_t* env, int T, const float* action, const int32_t* partner, const int32_t* ngroups,
+                             const int32_t* arrivals, const risvec_marl_out_t* out, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     if (env->dims.variant != RISVEC_VARIANT_MARL) return fail(RISVEC_ERR_INVALID, "handle is not a MARL env");
     if (T < 1) return fail(RISVEC_ERR_INVALID, "T must be >= 1 (got %d)", T);
@@ -759,6 +787,8 @@ int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int
                     CUDA_TRY(cudaFuncSetAttribute(k_marl_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMarlSmemBytes));
                     attr_set = true;
                 }
+                a.stats_slots = env->stats_slots;  // the statistics pass rides in the kernel's tail
+                env->stats_folded = env->stats_slots != nullptr;
                 k_marl_tma<<<E / 4, 128, kMarlSmemBytes, st>>>(env->dims, env->st, marl_consts(env->params), a, tm_ac, tm_ar, tm);
                 return check_step_launch(env, "k_marl_tma");
             }
@@ -780,8 +810,8 @@ int risvec_rollout_marl(risvec_env_t* env, int T, const float* action, const int
     }
 }
 
-int risvec_rollout_sarl(risvec_env_t* env, int T, const float* action, const float* phase, const int32_t* arrivals,
-                        const risvec_sarl_out_t* out, void* stream) {
+static int rollout_sarl_impl(risvec_env_t* env, int T, const float* action, const float* phase, const int32_t* arrivals,
+                             const risvec_sarl_out_t* out, void* stream) {
     if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
     if (env->dims.variant != RISVEC_VARIANT_SARL) return fail(RISVEC_ERR_INVALID, "handle is not a SARL env");
     if (T < 1) return fail(RISVEC_ERR_INVALID, "T must be >= 1 (got %d)", T);
@@ -938,9 +968,11 @@ int risvec_rollout_marl_host(risvec_env_t* env, int T, const float* action, cons
 #define OFF(member, per) oc.member = d_out.member ? d_out.member + o * (per) : nullptr
         OFF(reward_user, V); OFF(reward, 1); OFF(DataBuf, V); OFF(data_t, V); OFF(data_p, V); OFF(rate, V);
         OFF(over_power, V); OFF(stats, RISVEC_NSTAT); OFF(last_power, 2 * V);
-        if (int rc = risvec_rollout_marl(env, tn, d_act + o * 2 * V, d_part, d_ng, d_arr ? d_arr + o * V : nullptr, &oc,
-                                         stream))
-            return rc;
+        double* const slots = env->stats_slots;
+        if (t0 + tn < T) env->stats_slots = nullptr;  // the statistics are those of the rollout's last step
+        const int rc = risvec_rollout_marl(env, tn, d_act + o * 2 * V, d_part, d_ng, d_arr ? d_arr + o * V : nullptr, &oc, stream);
+        env->stats_slots = slots;
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ev_k[ci], st));
         CUDA_TRY(cudaStreamWaitEvent(so, ev_k[ci], 0));
 #define D2H(member, per) \
@@ -1003,9 +1035,11 @@ int risvec_rollout_sarl_host(risvec_env_t* env, int T, const float* action, cons
         memset(&oc, 0, sizeof(oc));
         OFF(reward, 1); OFF(DataBuf, V); OFF(data_t, V); OFF(data_p, V); OFF(over_power, V); OFF(over_data, V);
         OFF(rate, V);
-        if (int rc = risvec_rollout_sarl(env, tn, d_act + o * 2 * V, d_ph + o * M, d_arr ? d_arr + o * V : nullptr, &oc,
-                                         stream))
-            return rc;
+        double* const slots = env->stats_slots;
+        if (t0 + tn < T) env->stats_slots = nullptr;  // the statistics are those of the rollout's last step
+        const int rc = risvec_rollout_sarl(env, tn, d_act + o * 2 * V, d_ph + o * M, d_arr ? d_arr + o * V : nullptr, &oc, stream);
+        env->stats_slots = slots;
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ev_k[ci], st));
         CUDA_TRY(cudaStreamWaitEvent(so, ev_k[ci], 0));
         D2H(reward, 1); D2H(DataBuf, V); D2H(data_t, V); D2H(data_p, V); D2H(over_power, V); D2H(over_data, V);
@@ -1470,6 +1504,33 @@ int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* str
     if (blocks > 148) blocks = 148;
     k_shard_stats<<<blocks, 1024, 0, (cudaStream_t)stream>>>(env->dims, env->st, out);
     return check_launch(env, "k_shard_stats");
+}
+
+int risvec_attach_stats_accumulator(risvec_env_t* env, double* slots) {
+    if (!env) return fail(RISVEC_ERR_INVALID, "NULL handle");
+    if (((uintptr_t)slots) & 255u) return fail(RISVEC_ERR_INVALID, "the accumulator must be 256-byte aligned");
+    env->stats_slots = slots;
+    return RISVEC_OK;
+}
+}  // extern "C"
+namespace risvec {
+__global__ void k_collect_stats(double* __restrict__ slots, double* __restrict__ out, int accumulate) {
+    const int c = threadIdx.x;  // one thread per statistic: the 64 slots are summed in slot order, then cleared
+    if (c > RISVEC_NSTAT) return;
+    double acc = accumulate ? out[c] : 0.0;
+    for (int sl = 0; sl < kRisvecStatSlots; ++sl) {
+        acc += slots[sl * 32 + c];
+        slots[sl * 32 + c] = 0.0;
+    }
+    out[c] = acc;
+}
+}  // namespace risvec
+extern "C" {
+int risvec_collect_stats(risvec_env_t* env, double* slots, double* out, int accumulate, void* stream) {
+    if (!env || !slots || !out) return fail(RISVEC_ERR_INVALID, "NULL argument");
+    ENTER_DEVICE(env->device);
+    k_collect_stats<<<1, 32, 0, (cudaStream_t)stream>>>(slots, out, accumulate);
+    return check_launch(env, "k_collect_stats");
 }
 
 // ---- a device buffer other processes of the job can map (CUDA IPC over NVLink peer access)

@@ -690,6 +690,14 @@ __global__ void __launch_bounds__(128, RISVEC_TMA_MINB)
     if (g == ((T - 1) & 3) && tig == (((T - 1) & 15) >> 2)) s.reward[e] = fin.rew;
     if (tig == 0) s.databuf[ev] = buf;
     if (lane == 0) s.step_ctr[e] += T;
+    if (a.stats_slots != nullptr) {  // the statistics pass folded in: what k_shard_stats would sum after this launch
+        __shared__ float blk_rew[4];  // (SARL kernels write no `last_*` columns: the sum is the reward's)
+        if (g == ((T - 1) & 3) && tig == (((T - 1) & 15) >> 2)) blk_rew[warp] = fin.rew;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            atomicAdd(a.stats_slots + (blockIdx.x % kRisvecStatSlots) * 32 + RISVEC_NSTAT,
+                      ((double)blk_rew[0] + (double)blk_rew[1]) + ((double)blk_rew[2] + (double)blk_rew[3]));
+    }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
 }
 

@@ -14,6 +14,7 @@
 
 namespace risvec {
 
+constexpr int kRisvecStatSlots = 64;  // == RISVEC_STAT_SLOTS: one 256-byte line pair per slot
 struct MarlArgs {
     int T;
     const float* action;   // [T,E,2,V]
@@ -28,6 +29,9 @@ struct MarlArgs {
     // state after the last step, written in the epilogue
     const float* raw;
     float* obs;
+    // statistics accumulator attached to the handle (risvec_attach_stats_accumulator): kRisvecStatSlots slots of 32
+    // doubles; kernels that fold the statistics pass add the sums of their last step into slot blockIdx.x % slots
+    double* stats_slots;
 };
 
 struct SarlArgs {
@@ -45,6 +49,7 @@ struct SarlArgs {
     // get_state of the state after the last step, written in the epilogue
     const float* raw;
     float* obs;
+    double* stats_slots;  // as in MarlArgs
 };
 
 __device__ inline int draw_arrival(const Dims& d, int e, int v, long long step, float lam) {

@@ -503,3 +503,60 @@ def test_fused_sarl_driver_step_is_bit_identical_to_the_three_calls(V, M, inject
         assert torch.equal(obs_a, obs_b), f"observation differs at step {step}: {(obs_a - obs_b).abs().max()}"
         for name in ("DataBuf", "data_t", "data_p", "vehicle_rate", "reward", "over_power", "over_data", "phase_real", "data_r"):
             assert torch.equal(getattr(a, name), getattr(b, name)), f"{name} differs at step {step}"
+
+
+@pytest.mark.parametrize("variant,path,kernel,E", [("sarl", "mma", "k_sarl_mma_tma", 4096), ("sarl", "v8", "k_sarl_v8", 4096),
+                                                    ("marl", "tma", "k_marl_tma", 4096), ("marl", "v8", "k_marl_v8", 516)])
+def test_attached_statistics_accumulator_equals_shard_stats(variant, path, kernel, E):
+    """risvec_attach_stats_accumulator: the statistics pass folded into the rollout (k_sarl_mma_tma / k_marl_tma add
+    their last step's sums in the kernel tail; other kernels are followed by k_shard_stats) gives what a
+    shard_stats() call after every rollout gives (float64 sums of the same float32 values: order only)."""
+    import os
+
+    from ris_vec_marl_b200 import BatchedEnviron, encode_groups, marl_yaml_overrides
+    from tests.gpu_backend import sarl_path
+
+    V, M, T = 8, 40, 40
+    old = os.environ.get("RISVEC_MARL_PATH")
+    os.environ["RISVEC_MARL_PATH"] = path if variant == "marl" else "tma"
+    try:
+        with sarl_path(path if variant == "sarl" else "auto"):
+            over = marl_yaml_overrides() if variant == "marl" else {}
+            envs = [BatchedEnviron(variant, E, V, M, seed=9, **over) for _ in range(2)]
+    finally:
+        os.environ.pop("RISVEC_MARL_PATH", None) if old is None else os.environ.__setitem__("RISVEC_MARL_PATH", old)
+    rng = np.random.default_rng(5)
+    for env in envs:
+        env.make_new_game(); env.renew_positions(); env.compute_parms()
+        if variant == "marl":
+            env.optimize_phase_shift(); env.update_channel_gains()
+    a, b = envs
+    a.attach_stats_accumulator()
+    want = torch.zeros(17, dtype=torch.float64, device="cuda")
+    part, ng = encode_groups([[0, 1], [2, 3], [4], [5, 6], [7]], V)
+    partner = np.tile(part, (E, 1)); ngroups = np.full(E, ng, np.int32)
+    for r in range(3):
+        acts = rng.random((T, E, 2, V)).astype(np.float32)
+        arr = rng.poisson(2.0, (T, E, V)).astype(np.int32)
+        for env in envs:
+            if variant == "sarl":
+                phs = (np.random.default_rng(r).random((T, E, M)) * 6.28).astype(np.float32)
+                env.rollout_sarl(acts, phs, arr)
+            else:
+                env.rollout_marl(acts, partner, ngroups, arr, traces=("reward_user", "reward", "DataBuf", "data_t", "data_p", "rate"))
+        assert a.last_kernel() == kernel, a.last_kernel()
+        b.shard_stats(out=want, accumulate=True)
+    got = a.collect_stats()
+    assert torch.equal(a.collect_stats(), torch.zeros_like(got)), "collect clears the accumulator"
+    w = want.cpu().numpy(); g_ = got.cpu().numpy()
+    assert np.abs(w).max() > 0
+    np.testing.assert_allclose(g_, w, rtol=1e-12, atol=1e-9 * np.abs(w).max())
+    # the host-buffer form counts the last chunk only
+    if variant == "sarl" and path == "mma":
+        h = lambda x: torch.as_tensor(x).pin_memory()  # noqa: E731
+        out = {k: torch.empty((T, E) if k == "reward" else (T, E, V), dtype=torch.float32).pin_memory()
+               for k in ("reward", "DataBuf", "data_t", "data_p", "over_power", "over_data", "rate")}
+        a.rollout_sarl_host(h(acts), h(phs), h(arr), out)   # 2 chunks at this size (32 + 8 steps)
+        b.rollout_sarl(acts, phs, arr)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(a.collect_stats().cpu().numpy(), b.shard_stats().cpu().numpy(), rtol=1e-12, atol=1e-9)

@@ -350,12 +350,10 @@ int launch_sarl_umma(risvec_env* env, const SarlArgs& a, cudaStream_t st, bool* 
         tm_ar = tm_ac;  // unused: arrivals are drawn on the device
     else if (!tensor_map_2d(&tm_ar, CU_TENSOR_MAP_DATA_TYPE_INT32, a.arrivals, (uint64_t)E * V, T, V, 16))
         return RISVEC_OK;
-    static const uint32_t lbo = [] { const char* v = getenv("RISVEC_UMMA_LBO"); return v ? (uint32_t)atoi(v) : 128u; }();
-    static const uint32_t sbo = [] { const char* v = getenv("RISVEC_UMMA_SBO"); return v ? (uint32_t)atoi(v) : 256u; }();
     auto kern = k_sarl_umma<KQ>;
     const int smem = sarl_umma_smem_request(KQ, V);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<E, kUmmaThreads, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm, tm_ac, tm_ar, lbo, sbo);
+    kern<<<E, kUmmaThreads, smem, st>>>(env->dims, env->st, sarl_consts(env->params), a, tm, tm_ac, tm_ar);
     *launched = true;
     return check_step_launch(env, "k_sarl_umma");
 }

@@ -82,14 +82,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n"
@@ -118,8 +110,7 @@ template <int KQ>
 // (17 warps are allotted registers as 20: at most 96 per thread)
 __global__ void __launch_bounds__(kUmmaThreads, 1)
     k_sarl_umma(Dims d, State s, const SarlConsts c, SarlArgs a, const __grid_constant__ SarlBigOutMaps tm_out,
-                const __grid_constant__ CUtensorMap tm_ac, const __grid_constant__ CUtensorMap tm_ar, const uint32_t lbo,
-                const uint32_t sbo) {
+                const __grid_constant__ CUtensorMap tm_ac, const __grid_constant__ CUtensorMap tm_ar) {
     constexpr int KT = 4 * KQ, R = 16;
     constexpr int B_BYTES = KT * 1024, A_COLS = 8 * KT, TMEM_COLS = umma_tmem_cols(KQ);
     extern __shared__ unsigned char umma_smem_raw[];
@@ -522,7 +513,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
                 mbar_wait(bar_dempty + 8 * b, par ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_acc = tmem_d + (uint32_t)(D_COLS * b);
-                uint64_t bd = umma_desc(b_s + b * B_BYTES, lbo, sbo);
+                uint64_t bd = umma_desc(b_s + b * B_BYTES, 128u, 256u);  // core matrices 128 B apart along K, 8-row groups 256 B apart
                 for (int j = 0; j < kt_run; ++j) {
                     // A: 8 columns (16 K values) per k-step; D: chain j % kUmmaChains
                     umma_f16_ts(d_acc + 32 * (j % kUmmaChains), tmem + 8 * j, bd, kUmmaIdesc, j >= kUmmaChains);

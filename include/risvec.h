@@ -374,8 +374,8 @@ int risvec_replay_sample(risvec_replay_t* rb, int B, const int64_t* idx, float* 
 int risvec_shard_stats(risvec_env_t* env, double* out, int accumulate, void* stream);
 
 /* Statistics WITHOUT a separate pass per rollout.  `slots` = RISVEC_STAT_SLOTS (64) x 32 float64 (256-byte aligned,
- * zeroed by the caller), 17 used per slot.  Once attached, every risvec_rollout_sarl / _marl (and their _host forms:
- * the last chunk) adds the per-env statistics of its LAST step -- exactly what risvec_shard_stats would sum right
+ * zeroed by the caller), 17 used per slot.  Once attached, every risvec_rollout_sarl / _marl (their _host forms:
+ * the last chunk; the fused driver steps too; not the packed-record entry points) adds the per-env statistics of its LAST step -- exactly what risvec_shard_stats would sum right
  * after it -- into the slots: the tensor-core rollouts (k_sarl_mma_tma, k_marl_tma) do it in their last instructions
  * (one float64 atomic per block and statistic, slot = block index % 64, so concurrent blocks hit different L2
  * lines); every other kernel is followed by one k_shard_stats launch into slot 0.  NULL detaches.

@@ -1176,7 +1176,8 @@ int risvec_step_marl_fused(risvec_env_t* env, const float* raw, const int32_t* p
         memset(&a, 0, sizeof(a));
         a.T = 1; a.raw = raw; a.obs = obs; a.partner = partner; a.ngroups = ngroups; a.arrivals = arrivals;
         k_marl_v8<false, false, false, true><<<(d.E + 3) / 4, 32, 0, st>>>(d, env->st, env->params, a);
-        return check_step_launch(env, "k_marl_v8");
+        env->stats_folded = 0;  // an attached statistics accumulator is served by k_shard_stats
+        return finish_rollout(env, check_step_launch(env, "k_marl_v8"), stream);
     }
     // shapes the fused kernel does not take: the same three steps as separate launches (scratch action in the stage)
     if (int rc = ensure_stage(env, (size_t)d.E * 2 * d.V * 4 + 256)) return rc;
@@ -1206,7 +1207,8 @@ int risvec_step_sarl_fused(risvec_env_t* env, const float* raw, const int32_t* a
         else if (M <= 24) k_sarl_mma<3, false, true><<<blocks, 128, 0, st>>>(d, env->st, env->params, a);
         else if (M <= 40) k_sarl_mma<5, false, true><<<blocks, 128, 0, st>>>(d, env->st, env->params, a);
         else k_sarl_mma<8, false, true><<<blocks, 128, 0, st>>>(d, env->st, env->params, a);
-        return check_step_launch(env, "k_sarl_mma");
+        env->stats_folded = 0;  // an attached statistics accumulator is served by k_shard_stats
+        return finish_rollout(env, check_step_launch(env, "k_sarl_mma"), stream);
     }
     // shapes the fused kernel does not take: the same three steps as separate launches (scratch in the stage)
     if (int rc = ensure_stage(env, (size_t)d.E * (2 * d.V + d.M) * 4 + 512)) return rc;

@@ -521,10 +521,13 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     h0 = time.perf_counter()
     ev[0].record()
+    kev_every = int(os.environ.get("RISVEC_BENCH_KEV_EVERY", "1"))  # diagnostic: time every n-th launch only
     for i in range(args.steps):
-        kev[i][0].record()
+        if i % kev_every == 0:
+            kev[i][0].record()
         one_step()
-        kev[i][1].record()
+        if i % kev_every == 0:
+            kev[i][1].record()
         episode_stats()
     ev[1].record()
     h1 = time.perf_counter()
@@ -536,7 +539,7 @@ def main():
     stats_total = shared.read() if shared is not None else stats_sum.cpu()
     mean_reward = float(stats_total[16]) / (world * E * args.steps)
     ms_local = ev[0].elapsed_time(ev[2])
-    kern_ms = sorted(a.elapsed_time(b) for a, b in kev)
+    kern_ms = sorted(a.elapsed_time(b) for i, (a, b) in enumerate(kev) if i % kev_every == 0)
     kern_ms_avg = sum(kern_ms) / len(kern_ms)
     per_rank = ranks.gather([ms_local, kern_ms_avg, ev[1].elapsed_time(ev[2]), (h1 - h0) / args.steps * 1e6])
     ms_total = ranks.max(ms_local)
